@@ -1,0 +1,235 @@
+// chunk.cu -- build the device-resident chunk for the batched halo path.
+//
+// Replaces the per-ptype SharedMesh construction of
+// SOAP/core/chunk_tasks.py:299-304 for soap_process_halos: all particle types
+// are merged into one SoA particle set, binned by an internal fine mesh
+// (counting sort keyed by cell id, same arithmetic as shared_mesh.py:69-77) and
+// physically reordered into cell order, so that the sphere gather reads
+// contiguous, coalesced spans.  Membership never depends on the mesh: it is
+// decided by the exact periodic r2 test of shared_mesh.py:138-142,192.
+#include "chunk.cuh"
+
+int soap_mesh_bounds(soap_handle* h, const double* pos_dev, int64_t n, int resolution,
+                     double pos_min[3], double pos_max[3], double cell_size[3],
+                     cudaStream_t stream, bool guard);
+
+namespace {
+
+constexpr int TB = 256;
+
+struct Geom {
+    double pmin[3], cs[3];
+    int res;
+};
+
+__global__ void __launch_bounds__(TB) k_fine_hist(const double* __restrict__ pos, int64_t n, Geom g,
+                                                  uint32_t* __restrict__ key,
+                                                  uint32_t* __restrict__ rank,
+                                                  uint32_t* __restrict__ count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cx = cell_coord(pos[3 * i], g.pmin[0], g.cs[0], g.res);
+    int cy = cell_coord(pos[3 * i + 1], g.pmin[1], g.cs[1], g.res);
+    int cz = cell_coord(pos[3 * i + 2], g.pmin[2], g.cs[2], g.res);
+    uint32_t c = (uint32_t)cx + (uint32_t)g.res * ((uint32_t)cy + (uint32_t)g.res * (uint32_t)cz);
+    key[i] = c;
+    rank[i] = atomicAdd(&count[c], 1u);
+}
+
+struct SoAOut {
+    double *px, *py, *pz;
+    float *mass, *vx, *vy, *vz;
+    int32_t *grnr, *fof;
+    uint8_t* type;
+    uint32_t* orig;
+};
+
+template <bool ID64>
+__global__ void __launch_bounds__(TB) k_reorder(const double* __restrict__ pos,
+                                                const float* __restrict__ mass,
+                                                const float* __restrict__ vel,
+                                                const void* __restrict__ grnr,
+                                                const void* __restrict__ fof, int64_t n,
+                                                const uint32_t* __restrict__ key,
+                                                const uint32_t* __restrict__ rank,
+                                                const uint32_t* __restrict__ cell_off,
+                                                uint8_t tcode, SoAOut o) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d = cell_off[key[i]] + rank[i];
+    o.px[d] = pos[3 * i];
+    o.py[d] = pos[3 * i + 1];
+    o.pz[d] = pos[3 * i + 2];
+    o.mass[d] = mass[i];
+    o.vx[d] = vel[3 * i];
+    o.vy[d] = vel[3 * i + 1];
+    o.vz[d] = vel[3 * i + 2];
+    if (ID64) {
+        o.grnr[d] = (int32_t)((const int64_t*)grnr)[i];
+        o.fof[d] = (int32_t)((const int64_t*)fof)[i];
+    } else {
+        o.grnr[d] = ((const int32_t*)grnr)[i];
+        o.fof[d] = ((const int32_t*)fof)[i];
+    }
+    o.type[d] = tcode;
+    o.orig[d] = (uint32_t)i;
+}
+
+template <typename T>
+int dev_alloc(soap_chunk* c, T** p, size_t count) {
+    void* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, sizeof(T) * (count ? count : 1)));
+    c->owned.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_types,
+                      double boxsize, int fine_ppc, soap_chunk** out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!h || !types || !out) SOAP_FAIL("soap_chunk_create: NULL argument");
+    if (n_types < 1 || n_types > 4) SOAP_FAIL("soap_chunk_create: n_types=%d outside [1,4]", n_types);
+    CUDA_TRY(cudaSetDevice(h->device));
+    int64_t n = 0;
+    for (int t = 0; t < n_types; t++) {
+        if (types[t].n < 0) SOAP_FAIL("soap_chunk_create: negative particle count");
+        if (types[t].ptype != 0 && types[t].ptype != 1 && types[t].ptype != 4 && types[t].ptype != 5)
+            SOAP_FAIL("soap_chunk_create: ptype %d not in {0,1,4,5}", types[t].ptype);
+        n += types[t].n;
+    }
+    if (n <= 0) SOAP_FAIL("soap_chunk_create: no particles");
+    if (n >= (1ll << 32) - 2) SOAP_FAIL("soap_chunk_create: %lld particles exceed the 2^32 limit", (long long)n);
+    soap_chunk* c = new soap_chunk();
+    c->h = h;
+    c->create_log.reset();
+    c->create_log.begin("mesh_bounds", stream);
+    // exact bounding box over all types (shared_mesh.py:35-58 per ptype, merged)
+    double pmin[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
+    double pmax[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    for (int t = 0; t < n_types; t++) {
+        if (types[t].n == 0) continue;
+        double a[3], b[3], cs[3];
+        if (soap_mesh_bounds(h, types[t].pos, types[t].n, 1, a, b, cs, stream, false)) { delete c; return -1; }
+        for (int d = 0; d < 3; d++) {
+            pmin[d] = a[d] < pmin[d] ? a[d] : pmin[d];
+            pmax[d] = b[d] > pmax[d] ? b[d] : pmax[d];
+        }
+    }
+    c->create_log.end(stream);
+    if (fine_ppc <= 0) fine_ppc = 8;
+    int res = (int)cbrt((double)n / (double)fine_ppc);
+    if (res < 1) res = 1;
+    if (res > 512) res = 512;
+    ChunkView& v = c->v;
+    v.n = n;
+    v.L = boxsize;
+    v.res = res;
+    for (int d = 0; d < 3; d++) {
+        if (pmin[d] == pmax[d]) pmax[d] = pmin[d] + 1.0;
+        v.pmin[d] = pmin[d];
+        v.pmax[d] = pmax[d];
+        v.cs[d] = (pmax[d] - pmin[d]) / res;
+    }
+    const int64_t ncell = (int64_t)res * res * res;
+    SoAOut o;
+    uint32_t* cell_off = nullptr;
+    int rc = 0;
+    rc |= dev_alloc(c, &cell_off, ncell + 1);
+    rc |= dev_alloc(c, &o.px, n); rc |= dev_alloc(c, &o.py, n); rc |= dev_alloc(c, &o.pz, n);
+    rc |= dev_alloc(c, &o.mass, n);
+    rc |= dev_alloc(c, &o.vx, n); rc |= dev_alloc(c, &o.vy, n); rc |= dev_alloc(c, &o.vz, n);
+    rc |= dev_alloc(c, &o.grnr, n); rc |= dev_alloc(c, &o.fof, n);
+    rc |= dev_alloc(c, &o.type, n); rc |= dev_alloc(c, &o.orig, n);
+    if (rc) { soap_chunk_destroy(c); return -1; }
+    uint32_t* key = (uint32_t*)h->get("chunk_key", sizeof(uint32_t) * (size_t)n);
+    uint32_t* rank = (uint32_t*)h->get("chunk_rank", sizeof(uint32_t) * (size_t)n);
+    if (!key || !rank) { soap_chunk_destroy(c); return -1; }
+    Geom g;
+    for (int d = 0; d < 3; d++) { g.pmin[d] = v.pmin[d]; g.cs[d] = v.cs[d]; }
+    g.res = res;
+#define CK(stmt) do { if ((stmt) != 0) { soap_chunk_destroy(c); return -1; } } while (0)
+#define CKL(...) do { auto _f = [&]() -> int { __VA_ARGS__; return 0; }; if (_f() != 0) { soap_chunk_destroy(c); return -1; } } while (0)
+    c->create_log.begin("mesh_hist", stream);
+    CKL(CUDA_TRY(cudaMemsetAsync(cell_off, 0, sizeof(uint32_t) * (ncell + 1), stream)));
+    int64_t base = 0;
+    for (int t = 0; t < n_types; t++) {
+        if (types[t].n == 0) continue;
+        CKL(LAUNCH(h, k_fine_hist, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos, types[t].n, g,
+                   key + base, rank + base, cell_off));
+        base += types[t].n;
+    }
+    c->create_log.end(stream);
+    c->create_log.begin("mesh_scan", stream);
+    CK(soap_exclusive_scan_u32(h, cell_off, cell_off, nullptr, ncell + 1, nullptr, stream));
+    c->create_log.end(stream);
+    c->create_log.begin("reorder", stream);
+    base = 0;
+    for (int t = 0; t < n_types; t++) {
+        if (types[t].n == 0) continue;
+        uint8_t tc = (uint8_t)ptype_code(types[t].ptype);
+        c->type_present[tc] = 1;
+        if (types[t].ids_are_int64)
+            CKL(LAUNCH(h, k_reorder<true>, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos,
+                       types[t].mass, types[t].vel, types[t].grnr, types[t].fof, types[t].n, key + base,
+                       rank + base, cell_off, tc, o));
+        else
+            CKL(LAUNCH(h, k_reorder<false>, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos,
+                       types[t].mass, types[t].vel, types[t].grnr, types[t].fof, types[t].n, key + base,
+                       rank + base, cell_off, tc, o));
+        base += types[t].n;
+    }
+    c->create_log.end(stream);
+#undef CK
+#undef CKL
+    v.cell_off = cell_off;
+    v.px = o.px; v.py = o.py; v.pz = o.pz;
+    v.mass = o.mass; v.vx = o.vx; v.vy = o.vy; v.vz = o.vz;
+    v.grnr = o.grnr; v.fof = o.fof; v.type = o.type;
+    c->orig = o.orig;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        snprintf(g_soap_err, sizeof(g_soap_err), "soap_chunk_create: %s", cudaGetErrorString(e));
+        soap_chunk_destroy(c);
+        return -1;
+    }
+    c->create_log.collect();
+    *out = c;
+    return 0;
+}
+
+int soap_chunk_destroy(soap_chunk* c) {
+    if (!c) return 0;
+    for (void* p : c->owned) cudaFree(p);
+    delete c;
+    return 0;
+}
+
+int64_t soap_chunk_num_particles(const soap_chunk* c) { return c ? c->v.n : 0; }
+int64_t soap_chunk_last_pairs(const soap_chunk* c) { return c ? c->last_pairs : 0; }
+
+int64_t soap_chunk_timings(const soap_chunk* c, char* buf, int64_t buflen) {
+    if (!c || !buf || buflen <= 0) return 0;
+    std::string s;
+    char line[160];
+    for (auto& kv : c->create_log.ms) {
+        snprintf(line, sizeof(line), "create/%s:%.6f\n", kv.first.c_str(), kv.second);
+        s += line;
+    }
+    for (auto& kv : c->halo_log.ms) {
+        snprintf(line, sizeof(line), "halos/%s:%.6f\n", kv.first.c_str(), kv.second);
+        s += line;
+    }
+    snprintf(line, sizeof(line), "stat/pairs:%lld\nstat/candidates:%lld\nstat/rounds:%d\nstat/res:%d\n",
+             (long long)c->last_pairs, (long long)c->last_candidates, c->last_rounds, c->v.res);
+    s += line;
+    int64_t m = (int64_t)s.size() < buflen - 1 ? (int64_t)s.size() : buflen - 1;
+    memcpy(buf, s.data(), m);
+    buf[m] = 0;
+    return m;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// halos.cuh -- shared definitions of the batched halo pipeline (halos.cu, moments.cu)
+#pragma once
+#include "chunk.cuh"
+
+constexpr double SOAP_PI = 3.141592653589793;
+
+// property_flags bits (include/soap_b200.h)
+constexpr uint32_t PF_KIN = 1u, PF_KAPPA = 2u, PF_TENS = 4u, PF_HMR = 8u;
+
+// One in-sphere particle of one halo, the unit of the segmented radial sort.
+struct __align__(16) Rec {
+    unsigned long long rbits;  // IEEE bits of the float64 radius (non-negative: order-preserving)
+    float m;
+    uint32_t flags;            // bits 0-1 type code, bit 2 bound to this halo
+};
+
+// halo states of the radius ladder (SOAP/core/halo_tasks.py:73-187)
+enum : int32_t { ST_PENDING = 0, ST_TRY = 1, ST_FINAL = 2, ST_DONE_FAIL = 3 };
+
+// Result of the sorted-profile pass of one halo (global memory).
+struct ScanRes {
+    double so_r[SOAP_MAX_SO], so_mass[SOAP_MAX_SO];
+    double so_vmax_r[SOAP_MAX_SO], so_vmax_v[SOAP_MAX_SO];  // v = cum/r (times G later)
+    double so_dm_missed[SOAP_MAX_SO];
+    double sub_vmax_u_r, sub_vmax_u_v, sub_vmax_s_r, sub_vmax_s_v;
+    double sub_hmr[5];  // tot, gas, dm, star, baryon
+    double sub_enclose;
+    double ap_hmr[SOAP_MAX_APERTURES][4];  // gas, dm, star, baryon
+    double bound_mass[4];
+    uint32_t bound_count[4];
+    int32_t cen_fof;
+    int32_t so_exists[SOAP_MAX_SO];
+};
+
+// Selection block layout inside a result row (offsets relative to block start).
+struct BlockLayout {
+    int kin, kappa, tens, hmr, extra, size;
+};
+
+__host__ __device__ inline BlockLayout block_layout(uint32_t flags, int n_extra) {
+    BlockLayout b;
+    int o = 17;
+    b.kin = (flags & PF_KIN) ? o : -1;
+    if (flags & PF_KIN) o += 51;
+    b.kappa = (flags & PF_KAPPA) ? o : -1;
+    if (flags & PF_KAPPA) o += 5;
+    b.tens = (flags & PF_TENS) ? o : -1;
+    if (flags & PF_TENS) o += 12;
+    b.hmr = (flags & PF_HMR) ? o : -1;
+    if (flags & PF_HMR) o += 4;
+    b.extra = o;
+    b.size = o + n_extra;
+    return b;
+}
+constexpr int N_INPUT_COLS = 6;  // status, n_loop, radius, n_pairs, search_radius_out, read_radius_out
+constexpr int N_SUB_EXTRA = 5;   // HalfMassRadiusTot, EncloseRadius, Vmax_unsoft, R_vmax_unsoft, spin
+constexpr int N_SO_EXTRA = 9;    // r, SO_mass, spin, Mfrac_sat, Mfrac_ext, conc_unsoft, conc_soft, conc_dmo_unsoft, conc_dmo_soft
+
+struct RowLayout {
+    int ncol;
+    int sub;                       // -1 if absent
+    int so[SOAP_MAX_SO];
+    int ap[SOAP_MAX_APERTURES];
+    BlockLayout bsub, bso, bap;
+};
+
+inline RowLayout row_layout(const soap_halo_config& cfg) {
+    RowLayout L;
+    L.bsub = block_layout(cfg.property_flags, N_SUB_EXTRA);
+    L.bso = block_layout(cfg.property_flags, N_SO_EXTRA);
+    L.bap = block_layout(cfg.property_flags, 0);
+    int o = N_INPUT_COLS;
+    L.sub = -1;
+    if (cfg.do_subhalo) { L.sub = o; o += L.bsub.size; }
+    for (int k = 0; k < SOAP_MAX_SO; k++) {
+        L.so[k] = -1;
+        if (k < cfg.n_so) { L.so[k] = o; o += L.bso.size; }
+    }
+    for (int a = 0; a < SOAP_MAX_APERTURES; a++) {
+        L.ap[a] = -1;
+        if (a < cfg.n_apertures) { L.ap[a] = o; o += L.bap.size; }
+    }
+    L.ncol = o;
+    return L;
+}
+
+// Device-side copy of what the kernels need from soap_halo_config.
+struct DevCfg {
+    double L, halfL, G, H, kpc, r20, nu, mpc2c;
+    double soft[4];  // by type code
+    double target_density;
+    int do_sub, n_so, n_ap, dmo;
+    double so_rho[SOAP_MAX_SO];
+    int so_virial[SOAP_MAX_SO];
+    double ap_r[SOAP_MAX_APERTURES], ap_mpc[SOAP_MAX_APERTURES];
+    int ap_incl[SOAP_MAX_APERTURES];
+    uint32_t flags;
+    RowLayout lay;
+};
+
+// Per-halo arrays (inputs are caller memory, the rest is workspace).
+struct HaloArrays {
+    const double* cofp;
+    const double* sr_in;
+    const double* rr_in;
+    const int64_t* index;
+    const int32_t* central;
+    const int64_t* nexp;
+    double* cur_r;
+    int32_t* nloop;
+    int32_t* state;
+    int32_t* status;
+    uint32_t* cnt;
+    double* msum;
+    unsigned long long* rec_off;
+    uint32_t* fine_off;
+    uint32_t* nfine;
+    double* required;  // required radius of the failing property of this rung
+    ScanRes* sres;
+    double* out;
+    int64_t ncol;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int range_total(const DimRanges& r) {
+    int t = 0;
+    for (int a = 0; a < r.n; a++) t += r.hi[a] - r.lo[a] + 1;
+    return t;
+}
+__device__ __forceinline__ int range_cell(const DimRanges& r, int idx) {
+    for (int a = 0; a < r.n; a++) {
+        int len = r.hi[a] - r.lo[a] + 1;
+        if (idx < len) return r.lo[a] + idx;
+        idx -= len;
+    }
+    return r.lo[0];
+}
+
+// Row = one run of cells along x for fixed (y, z): a contiguous particle span.
+struct RowIter {
+    int ny, nx, nrows;
+};
+__device__ __forceinline__ RowIter row_iter(const DimRanges* rg) {
+    RowIter it;
+    it.ny = range_total(rg[1]);
+    it.nx = rg[0].n;
+    it.nrows = range_total(rg[2]) * it.ny * it.nx;
+    return it;
+}
+__device__ __forceinline__ void row_span(const ChunkView& v, const DimRanges* rg, const RowIter& it,
+                                         int row, uint32_t& s0, uint32_t& s1) {
+    int rx = row % it.nx;
+    int t = row / it.nx;
+    int jy = range_cell(rg[1], t % it.ny);
+    int kz = range_cell(rg[2], t / it.ny);
+    uint32_t c0 = (uint32_t)rg[0].lo[rx] + (uint32_t)v.res * ((uint32_t)jy + (uint32_t)v.res * (uint32_t)kz);
+    uint32_t c1 = c0 + (uint32_t)(rg[0].hi[rx] - rg[0].lo[rx]);
+    s0 = v.cell_off[c0];
+    s1 = v.cell_off[c1 + 1];
+}
+__device__ __forceinline__ void halo_ranges(const ChunkView& v, double cx, double cy, double cz,
+                                            double r, DimRanges* rg) {
+    // called by threads 0..2
+    int d = threadIdx.x;
+    double c = d == 0 ? cx : (d == 1 ? cy : cz);
+    dim_ranges(c, r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
+}
+#endif

@@ -1,0 +1,70 @@
+"""GPU parity of the batched halo path (stage B+C) against the oracle."""
+
+import numpy as np
+import pytest
+
+from soap_b200 import synth
+from tests import _compare as cmp
+
+pytestmark = pytest.mark.gpu
+
+SO4 = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
+
+
+def _run(data, H, cp, so, apertures, flags, dmo, fine_ppc=0, halos=None):
+    from soap_b200.halo_tasks import DeviceChunk, process_halos
+
+    cfg = cmp.device_config(cp, so=so, apertures=apertures, flags=flags, dmo=dmo)
+    chunk = DeviceChunk(data, cp["boxsize"], fine_ppc=fine_ppc)
+    res = process_halos(chunk, cfg, H)
+    oracle_out, props = cmp.run_oracle(data, H, cp, so, apertures, faithful=False, halos=halos)
+    rep = cmp.compare(res, oracle_out, props, cp, halos=halos, flags=flags)
+    print("max errors:", {k: float(f"{v:.3g}") for k, v in sorted(rep.maxerr.items())})
+    print("timings:", chunk.timings())
+    rep.assert_ok()
+    return res, rep
+
+
+def test_dmo_nfw_chunk_so_and_subhalo():
+    L = 40.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.to_numpy(*synth.nfw_chunk(400000, 400, L, seed=1, max_np=20000))
+    _run(data, H, cp, SO4, [], flags=cmp_flags(hmr=True), dmo=True)
+
+
+def test_dmo_nfw_chunk_fine_mesh_independent():
+    """membership and results must not depend on the internal mesh resolution"""
+    L = 30.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.to_numpy(*synth.nfw_chunk(150000, 150, L, seed=3, max_np=30000))
+    for ppc in (1, 64, 100000):
+        _run(data, H, cp, SO4[:2], [], flags=0, dmo=True, fine_ppc=ppc)
+
+
+def test_dummy_chunk_all_types_apertures():
+    """reference-fixture-like halos (all particle types, satellites, unbound
+    particles, halos across the periodic edge) with SO + exclusive/inclusive
+    apertures + kinematics + tensors + half-mass radii"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(4251, 40, boxsize=L, n_background=200000,
+                                npart_choices=(1, 10, 100, 1000, 10000))
+    aps = []
+    for kpc in (30.0, 100.0):
+        for incl in (0, 1):
+            aps.append((kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl))
+    _run(data, H, cp, SO4[:3], aps, flags=1 | 4 | 8, dmo=False)
+
+
+def test_read_radius_too_small_status():
+    """halos that cannot reach the target density inside read_radius come back
+    with status 1 and the reference's updated radii (halo_tasks.py:166-181)"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(77, 12, boxsize=L, n_background=0, npart_choices=(100, 1000))
+    H["read_radius"][:] = np.maximum(H["search_radius"], 0.3)
+    _run(data, H, cp, SO4[:1], [], flags=0, dmo=False)
+
+
+def cmp_flags(kin=False, tens=False, hmr=False):
+    return (1 if kin else 0) | (4 if tens else 0) | (8 if hmr else 0)
