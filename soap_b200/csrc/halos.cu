@@ -52,6 +52,9 @@ __global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* pend) {
     ha.nloop[h] = 0;
     ha.state[h] = ST_PENDING;
     ha.status[h] = SOAP_HALO_OK;
+    ha.ndone[h] = 0;
+    ha.commit_lo[h] = 0;
+    ha.commit_hi[h] = 0;
     pend[h] = (uint32_t)h;
     double* row = ha.out + h * ha.ncol;
     for (int64_t c = 0; c < ha.ncol; c++) row[c] = 0.0;
@@ -828,20 +831,28 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
         __shared__ int s_fail;       // 0 ok, 1 retry, >=2 fatal status
         __shared__ double s_required;
         __shared__ double s_so_r[SOAP_MAX_SO];
+        __shared__ int s_commit_lo, s_commit_hi;
         if (threadIdx.x == 0) {
             int fail = 0;
             double required = 0.0;
             int status = SOAP_HALO_OK;
-            // 1. BoundSubhalo particle count (subhalo_properties.py:2632-2646)
-            if (cfg.do_sub) {
-                long long Ntot = NB, Nexp = ha.nexp[h];
-                if (Ntot < Nexp) { fail = 1; required = 0.0; }
-                else if (Ntot > Nexp) { fail = 2; status = SOAP_HALO_COUNT_MISMATCH; }
-            }
-            // 2. spherical overdensities in list order
+            // halo_prop_list order: BoundSubhalo, SO..., apertures.  Properties
+            // done at an earlier rung are not recomputed (halo_tasks.py:120-123),
+            // and the done set is always a prefix of the list.
+            const int off_so = cfg.do_sub ? 1 : 0, off_ap = off_so + cfg.n_so, nprops = off_ap + n_ap;
+            const int p0 = ha.ndone[h];
+            int p = p0;
             const double r_last = n > 0 ? __longlong_as_double((long long)R[n - 1].rbits) : 0.0;
             for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; s_so_r[q] = 0.0; }
-            for (int q = 0; q < n_so && !fail; q++) {
+            while (p < nprops && !fail) {
+                if (p < off_so) {
+                    // BoundSubhalo particle count (subhalo_properties.py:2632-2646)
+                    long long Ntot = NB, Nexp = ha.nexp[h];
+                    if (Ntot < Nexp) { fail = 1; required = 0.0; }
+                    else if (Ntot > Nexp) { fail = 2; status = SOAP_HALO_COUNT_MISMATCH; }
+                } else if (p < off_ap) {
+                    const int q = p - off_so;
+                    if (central) {
                 const double rho = cfg.so_rho[q];
                 double SO_r = 0.0, SO_mass = 0.0;
                 const uint32_t nr_parts = n > nskip_so ? n - nskip_so : 0u;
@@ -902,10 +913,22 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     sr->so_exists[q] = (SO_r > 0.0 && SO_mass > 0.0) ? 1 : 0;  // SO_properties.py:457
                     s_so_r[q] = sr->so_exists[q] ? SO_r : 0.0;
                 }
+                    }
+                } else {
+                    // apertures ascending (aperture_properties.py:4140-4143)
+                    const int a = p - off_ap;
+                    if (ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+                }
+                if (!fail) p++;
             }
-            // 3. apertures ascending (aperture_properties.py:4140-4143)
-            for (int a = 0; a < n_ap && !fail; a++)
-                if (ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+            ha.commit_lo[h] = p0;
+            ha.commit_hi[h] = p;
+            ha.ndone[h] = p;
+            s_commit_lo = p0;
+            s_commit_hi = p;
+            if (!fail && p >= nprops) {
+                (ha.out + (int64_t)h * ha.ncol)[3] = (double)n;
+            }
             s_fail = fail;
             s_required = required;
             if (fail >= 2) {
@@ -916,6 +939,8 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             } else {
                 ha.state[h] = ST_FINAL;
                 atomicAdd(&ctr->pairs, (unsigned long long)n);
+            }
+            if (fail < 2 && cfg.do_sub && s_commit_lo == 0 && s_commit_hi >= 1) {
                 // subhalo scan results
                 sr->sub_vmax_u_r = amU.i == NONE ? 0.0 : amU.r;
                 sr->sub_vmax_u_v = amU.i == NONE ? 0.0 : amU.v;
@@ -963,8 +988,11 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             }
         }
         __syncthreads();
-        const bool final_ok = s_fail == 0;
-        const bool need_c = final_ok && (n_so > 0 || (n_ap > 0 && want_hmr));
+        // pass C serves the SOs and apertures committed at this rung
+        const int c_so_lo = cfg.do_sub ? 1 : 0, c_ap_lo = c_so_lo + cfg.n_so;
+        const bool so_committed = n_so > 0 && s_commit_hi > s_commit_lo && s_commit_lo < c_ap_lo && s_commit_hi > c_so_lo;
+        const bool ap_committed = n_ap > 0 && s_commit_hi > c_ap_lo && s_commit_hi > s_commit_lo;
+        const bool need_c = s_fail < 2 && (so_committed || (ap_committed && want_hmr));
         if (!need_c) continue;
 
         // ------------------------------------------------------------ pass C
@@ -1248,6 +1276,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(fine_off, uint32_t, h, "h_fine_off", H); ha.fine_off = fine_off;
     WS_GET(nfine, uint32_t, h, "h_nfine", H); ha.nfine = nfine;
     WS_GET(required, double, h, "h_required", H); ha.required = required;
+    WS_GET(ndone, int32_t, h, "h_ndone", H); ha.ndone = ndone;
+    WS_GET(commit_lo, int32_t, h, "h_commit_lo", H); ha.commit_lo = commit_lo;
+    WS_GET(commit_hi, int32_t, h, "h_commit_hi", H); ha.commit_hi = commit_hi;
     WS_GET(sres, ScanRes, h, "h_sres", H); ha.sres = sres;
     WS_GET(listA, uint32_t, h, "h_listA", H);
     WS_GET(listB, uint32_t, h, "h_listB", H);

@@ -197,7 +197,11 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
     __shared__ Cuts cuts;
     for (unsigned int it = blockIdx.x; it < *n_try; it += gridDim.x) {
         const uint32_t h = try_list[it];
-        if (ha.state[h] != ST_FINAL) continue;
+        // properties [lo, hi) of halo_prop_list were computed at this rung
+        const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+        if (c_hi <= c_lo || ha.status[h] >= 2) continue;
+        const int off_so = cfg.do_sub ? 1 : 0, off_ap = off_so + cfg.n_so;
+        const bool sub_c = cfg.do_sub && c_lo == 0;
         const ScanRes* sr = ha.sres + h;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.cur_r[h];
@@ -210,16 +214,18 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
         if (threadIdx.x == 32) {
             Cuts& c = cuts;
             c.n = 0;
+            auto so_c = [&](int q) { return q < n_so && off_so + q >= c_lo && off_so + q < c_hi && sr->so_exists[q]; };
+            auto ap_c = [&](int a) { return a < cfg.n_ap && off_ap + a >= c_lo && off_ap + a < c_hi; };
             for (int q = 0; q < n_so; q++)
-                if (sr->so_exists[q]) add_cut(c, sr->so_r[q], 1, nullptr);
-            if (cfg.do_sub && sr->sub_vmax_s_r > 0.0) add_cut(c, sr->sub_vmax_s_r, 0, nullptr);
-            for (int a = 0; a < cfg.n_ap; a++) add_cut(c, cfg.ap_r[a], 0, nullptr);
-            if (cfg.do_sub && (cfg.flags & PF_TENS)) add_cut(c, 10.0 * sr->sub_hmr[0], 0, nullptr);
-            for (int q = 0; q < SOAP_MAX_SO; q++)
-                c.pos_so[q] = (q < n_so && sr->so_exists[q]) ? find_cut(c, sr->so_r[q], 1) : -1;
-            c.pos_vmax = (cfg.do_sub && sr->sub_vmax_s_r > 0.0) ? find_cut(c, sr->sub_vmax_s_r, 0) : -1;
-            for (int a = 0; a < SOAP_MAX_APERTURES; a++) c.pos_ap[a] = a < cfg.n_ap ? find_cut(c, cfg.ap_r[a], 0) : -1;
-            c.pos_tens = (cfg.do_sub && (cfg.flags & PF_TENS)) ? find_cut(c, 10.0 * sr->sub_hmr[0], 0) : -1;
+                if (so_c(q)) add_cut(c, sr->so_r[q], 1, nullptr);
+            if (sub_c && sr->sub_vmax_s_r > 0.0) add_cut(c, sr->sub_vmax_s_r, 0, nullptr);
+            for (int a = 0; a < cfg.n_ap; a++)
+                if (ap_c(a)) add_cut(c, cfg.ap_r[a], 0, nullptr);
+            if (sub_c && (cfg.flags & PF_TENS)) add_cut(c, 10.0 * sr->sub_hmr[0], 0, nullptr);
+            for (int q = 0; q < SOAP_MAX_SO; q++) c.pos_so[q] = so_c(q) ? find_cut(c, sr->so_r[q], 1) : -1;
+            c.pos_vmax = (sub_c && sr->sub_vmax_s_r > 0.0) ? find_cut(c, sr->sub_vmax_s_r, 0) : -1;
+            for (int a = 0; a < SOAP_MAX_APERTURES; a++) c.pos_ap[a] = ap_c(a) ? find_cut(c, cfg.ap_r[a], 0) : -1;
+            c.pos_tens = (sub_c && (cfg.flags & PF_TENS)) ? find_cut(c, 10.0 * sr->sub_hmr[0], 0) : -1;
         }
         __syncthreads();
         const int ncut = cuts.n;
@@ -295,8 +301,7 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
             double S[4][V];
             const int sel = threadIdx.x;
             if (sel == 0) {
-                row[3] = (double)ha.cnt[h];
-                if (cfg.do_sub) {
+                if (sub_c) {
                     for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, ncut, true, 1u << t, S[t]);
                     double* blk = row + L.sub;
                     write_block<V>(blk, L.bsub, S, centre, cfg, cfg.flags);
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
                 }
             } else if (sel <= SOAP_MAX_SO) {
                 const int q = sel - 1;
-                if (q < n_so && sr->so_exists[q]) {
+                if (q < n_so && cuts.pos_so[q] >= 0) {
                     const int pos = cuts.pos_so[q];
                     for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, pos, false, 1u << t, S[t]);
                     double* blk = row + L.so[q];
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
                 }
             } else {
                 const int a = sel - 1 - SOAP_MAX_SO;
-                if (a < cfg.n_ap) {
+                if (a < cfg.n_ap && cuts.pos_ap[a] >= 0) {
                     const int pos = cuts.pos_ap[a];
                     const bool excl = cfg.ap_incl[a] == 0;
                     for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, pos, excl, 1u << t, S[t]);
