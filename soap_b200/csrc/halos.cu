@@ -41,7 +41,7 @@ struct Counters {
     unsigned int n_try, n_next, n_multi, n_fine;
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, pad;
-    unsigned long long pairs, candidates;
+    unsigned long long pairs, candidates, count_pairs, mom_pairs;
 };
 
 // ------------------------------------------------------------------ k_init
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const 
             ha.cnt[h] = (uint32_t)c;
             ha.msum[h] = m;
             atomicAdd(&ctr->candidates, cd);
+            atomicAdd(&ctr->count_pairs, c);
         }
     }
 }
@@ -926,6 +927,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             ha.ndone[h] = p;
             s_commit_lo = p0;
             s_commit_hi = p;
+            if (p > p0 && fail < 2) atomicAdd(&ctr->mom_pairs, (unsigned long long)n);
             if (!fail && p >= nprops) {
                 (ha.out + (int64_t)h * ha.ncol)[3] = (double)n;
             }
@@ -1304,7 +1306,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                                       (int)(SB_CAP * sizeof(Rec))));
         attr_done = true;
     }
-    unsigned long long total_pairs = 0, total_cand = 0;
+    unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
     while (n_pend > 0) {
         c->last_rounds++;
         if (c->last_rounds > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
@@ -1321,6 +1323,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         total_cand += hc.candidates;
+        total_count_pairs += hc.count_pairs;
+        total_try_pairs += hc.rec_total;
         if (hc.n_try > 0) {
             const unsigned int n_try = hc.n_try;
             // workspace for this round
@@ -1384,6 +1388,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         CUDA_TRY(cudaMemcpyAsync(&hc2, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         total_pairs += hc2.pairs;
+        total_mom_pairs += hc2.mom_pairs;
         n_pend = hc2.n_next;
         uint32_t* t = pend; pend = next; next = t;
     }
@@ -1392,6 +1397,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     log.collect();
     c->last_pairs = (int64_t)total_pairs;
     c->last_candidates = (int64_t)total_cand;
+    c->last_count_pairs = (int64_t)total_count_pairs;
+    c->last_try_pairs = (int64_t)total_try_pairs;
+    c->last_mom_pairs = (int64_t)total_mom_pairs;
     return 0;
 }
 
