@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(TB) k_reorder(const double* __restrict__ pos,
 template <typename T>
 int dev_alloc(soap_chunk* c, T** p, size_t count) {
     void* q = nullptr;
-    CUDA_TRY(cudaMalloc(&q, sizeof(T) * (count ? count : 1)));
+    // stream-ordered pool allocation: after the first chunk no driver malloc/free per step
+    CUDA_TRY(cudaMallocAsync(&q, sizeof(T) * (count ? count : 1), c->stream));
     c->owned.push_back(q);
     *p = (T*)q;
     return 0;
@@ -105,6 +106,7 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     if (n >= (1ll << 32) - 2) SOAP_FAIL("soap_chunk_create: %lld particles exceed the 2^32 limit", (long long)n);
     soap_chunk* c = new soap_chunk();
     c->h = h;
+    c->stream = stream;
     c->create_log.reset();
     c->create_log.begin("mesh_bounds", stream);
     // exact bounding box over all types (shared_mesh.py:35-58 per ptype, merged)
@@ -203,7 +205,7 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
 
 int soap_chunk_destroy(soap_chunk* c) {
     if (!c) return 0;
-    for (void* p : c->owned) cudaFree(p);
+    for (void* p : c->owned) cudaFreeAsync(p, c->stream);
     delete c;
     return 0;
 }

@@ -57,6 +57,7 @@ struct PhaseLog {
 
 struct soap_chunk {
     soap_handle* h = nullptr;
+    cudaStream_t stream = nullptr;
     ChunkView v{};
     std::vector<void*> owned;  // device allocations freed at destroy
     uint32_t* orig = nullptr;  // [n] index within the particle's own ptype array

@@ -18,9 +18,9 @@
 //   k_moments      (moments.cu) masked moment sums + result row
 #include "halos.cuh"
 
-int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha,
-                        const uint32_t* try_list, const uint32_t* n_try_dev, uint32_t n_try_host,
-                        cudaStream_t stream);
+int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
+                        const unsigned int* n_items_dev, unsigned int n_items_host,
+                        unsigned int n_mslot, unsigned int grid, cudaStream_t stream);
 int soap_write_input_cols(soap_handle* h, const HaloArrays& ha, int64_t nh, cudaStream_t stream);
 
 namespace {
@@ -40,7 +40,8 @@ struct Bucket {
 struct Counters {
     unsigned int n_try, n_next, n_multi, n_fine;
     unsigned long long rec_single, rec_total;
-    unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, pad;
+    unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
+    unsigned int n_mslot, items_overflow;
     unsigned long long pairs, candidates, count_pairs, mom_pairs;
 };
 
@@ -55,57 +56,102 @@ __global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* pend) {
     ha.ndone[h] = 0;
     ha.commit_lo[h] = 0;
     ha.commit_hi[h] = 0;
+    ha.mslot[h] = -1;
     pend[h] = (uint32_t)h;
     double* row = ha.out + h * ha.ncol;
     for (int64_t c = 0; c < ha.ncol; c++) row[c] = 0.0;
 }
 
+// ------------------------------------------------------------- k_plan_items
+// One thread per pending halo: count the candidates of its rows at the current
+// radius and cut the candidate stream into work items of ITEM_CAND particles.
+__global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
+                                                    const unsigned int* __restrict__ n_pend,
+                                                    Item* __restrict__ items, unsigned int items_cap,
+                                                    Counters* ctr) {
+    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_pend) return;
+    const uint32_t h = pend[it];
+    DimRanges rg[3];
+    const double r = ha.cur_r[h];
+    for (int d = 0; d < 3; d++)
+        dim_ranges(ha.cofp[3 * h + d], r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
+    const RowIter ri = row_iter(rg);
+    unsigned long long cand = 0;
+    for (int row = 0; row < ri.nrows; row++) {
+        uint32_t s0, s1;
+        row_span(v, rg, ri, row, s0, s1);
+        cand += s1 - s0;
+    }
+    if (cand > 0xfffffff0ull) cand = 0xfffffff0ull;
+    uint32_t ni = (uint32_t)((cand + ITEM_CAND - 1) / ITEM_CAND);
+    if (ni < 1) ni = 1;
+    uint32_t base = atomicAdd(&ctr->n_items, ni);
+    if (base + ni > items_cap) {
+        atomicExch(&ctr->items_overflow, 1u);
+        ni = base < items_cap ? 1u : 0u;  // degrade: a single item covers the whole stream
+    }
+    ha.item_base[h] = base;
+    ha.n_items[h] = ni;
+    ha.cnt[h] = 0;
+    ha.msum[h] = 0.0;
+    ha.rung_r[h] = r;
+    ha.cursor[h] = 0;
+    ha.items_done[h] = 0;
+    ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+    ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
+    for (uint32_t k = 0; k < ni; k++) {
+        Item im;
+        im.halo = h;
+        im.first = k * ITEM_CAND;
+        im.count = (ni == 1) ? (uint32_t)cand : (uint32_t)((cand - (unsigned long long)k * ITEM_CAND) < ITEM_CAND ? (cand - (unsigned long long)k * ITEM_CAND) : ITEM_CAND);
+        im.pad = k;
+        items[base + k] = im;
+    }
+    atomicAdd(&ctr->candidates, cand);
+}
+
 // ----------------------------------------------------------------- k_count
-// One CTA per pending halo; a warp takes a row (contiguous span), lanes stride.
-__global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
-                                              const unsigned int* __restrict__ n_pend, Counters* ctr) {
-    __shared__ DimRanges rg[3];
-    __shared__ unsigned long long s_cnt[TB / 32], s_cand[TB / 32];
+// periodic sphere count + enclosed mass of every pending halo at its current
+// radius (halo_tasks.py:84-97; shared_mesh.py:122-200)
+__global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
+                                              Counters* ctr) {
+    __shared__ SweepShared S;
+    __shared__ unsigned long long s_cnt[TB / 32];
     __shared__ double s_m[TB / 32];
-    for (unsigned int it = blockIdx.x; it < *n_pend; it += gridDim.x) {
-        const uint32_t h = pend[it];
+    const unsigned int n_items = ctr->n_items;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double r = ha.cur_r[h];
         const double r2max = __dmul_rn(r, r);
-        const double halfL = 0.5 * v.L;
-        __syncthreads();
-        if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, r, rg);
-        __syncthreads();
-        const RowIter ri = row_iter(rg);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        unsigned long long cnt = 0, cand = 0;
+        const double halfL = 0.5 * v.L, L = v.L;
+        unsigned long long cnt = 0;
         double msum = 0.0;
-        for (int row = wid; row < ri.nrows; row += TB / 32) {
-            uint32_t s0, s1;
-            row_span(v, rg, ri, row, s0, s1);
-            cand += (lane == 0) ? (unsigned long long)(s1 - s0) : 0ull;
-            for (uint32_t t = s0 + lane; t < s1; t += 32) {
-                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, v.L, halfL);
+        sweep_item<TB>(v, S, cx, cy, cz, r, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+            if (ok) {
+                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
                 if (r2 <= r2max) {
                     cnt++;
                     msum += (double)v.mass[t];
                 }
             }
-        }
+        });
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         cnt = warp_sum_u64(cnt);
-        cand = warp_sum_u64(cand);
         msum = warp_sum(msum);
-        if (lane == 0) { s_cnt[wid] = cnt; s_cand[wid] = cand; s_m[wid] = msum; }
+        if (lane == 0) { s_cnt[wid] = cnt; s_m[wid] = msum; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long c = 0, cd = 0;
+            unsigned long long c = 0;
             double m = 0.0;
-            for (int w = 0; w < TB / 32; w++) { c += s_cnt[w]; cd += s_cand[w]; m += s_m[w]; }
-            ha.cnt[h] = (uint32_t)c;
-            ha.msum[h] = m;
-            atomicAdd(&ctr->candidates, cd);
+            for (int w = 0; w < TB / 32; w++) { c += s_cnt[w]; m += s_m[w]; }
+            if (c) atomicAdd(&ha.cnt[h], (unsigned int)c);
+            if (m != 0.0) atomicAdd(&ha.msum[h], m);
             atomicAdd(&ctr->count_pairs, c);
         }
+        __syncthreads();
     }
 }
 
@@ -185,34 +231,29 @@ __device__ __forceinline__ uint32_t fine_bin(double r, double R, uint32_t nf) {
 }
 
 // -------------------------------------------------------------- fine hist
-__global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays ha,
-                                                       const uint32_t* __restrict__ multi_list,
-                                                       const unsigned int* __restrict__ n_multi,
+__global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
+                                                       const Counters* __restrict__ ctr,
                                                        uint32_t* __restrict__ fine_cnt) {
-    __shared__ DimRanges rg[3];
-    for (unsigned int it = blockIdx.x; it < *n_multi; it += gridDim.x) {
-        const uint32_t h = multi_list[it];
+    __shared__ SweepShared S;
+    const unsigned int n_items = ctr->n_items;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
+        if (ha.state[h] != ST_TRY || ha.nfine[h] == 0) continue;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.cur_r[h];
-        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L;
+        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
         const uint32_t nf = ha.nfine[h];
         uint32_t* fc = fine_cnt + ha.fine_off[h];
-        __syncthreads();
-        if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, R, rg);
-        __syncthreads();
-        const RowIter ri = row_iter(rg);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int row = wid; row < ri.nrows; row += TB / 32) {
-            uint32_t s0, s1;
-            row_span(v, rg, ri, row, s0, s1);
-            for (uint32_t t = s0 + lane; t < s1; t += 32) {
-                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, v.L, halfL);
+        sweep_item<TB>(v, S, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+            if (ok) {
+                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
                 if (r2 <= r2max) {
                     Part p = rel_part(v, t, cx, cy, cz, halfL);
                     atomicAdd(&fc[fine_bin(p.r, R, nf)], 1u);
                 }
             }
-        }
+        });
     }
 }
 
@@ -271,80 +312,78 @@ __global__ void k_single_buckets(HaloArrays ha, const uint32_t* __restrict__ try
 
 // ---------------------------------------------------------------- k_collect
 __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevCfg cfg,
-                                                const uint32_t* __restrict__ try_list,
-                                                const unsigned int* __restrict__ n_try,
+                                                const Item* __restrict__ items,
                                                 const int64_t* __restrict__ fine_excl,
                                                 uint32_t* __restrict__ fine_cursor,
-                                                const Counters* __restrict__ ctr, Rec* __restrict__ recs) {
-    __shared__ DimRanges rg[3];
-    __shared__ unsigned int s_cursor;
+                                                const Counters* __restrict__ ctr, Rec* __restrict__ recs,
+                                                unsigned long long* __restrict__ item_minr,
+                                                int32_t* __restrict__ item_minfof) {
+    __shared__ SweepShared S;
     __shared__ unsigned long long s_minr[TB / 32];
     __shared__ int s_minfof[TB / 32];
-    for (unsigned int it = blockIdx.x; it < *n_try; it += gridDim.x) {
-        const uint32_t h = try_list[it];
+    const unsigned int n_items = ctr->n_items;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
+        if (ha.state[h] != ST_TRY) continue;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.cur_r[h];
-        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L;
+        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
         const uint32_t nf = ha.nfine[h];
         const int32_t hidx = (int32_t)ha.index[h];
         Rec* out = recs + (nf ? ctr->rec_single : ha.rec_off[h]);
         const int64_t* fex = fine_excl + (nf ? ha.fine_off[h] : 0);
         uint32_t* fcur = fine_cursor + (nf ? ha.fine_off[h] : 0);
-        __syncthreads();
-        if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, R, rg);
-        if (threadIdx.x == 0) s_cursor = 0;
-        __syncthreads();
-        const RowIter ri = row_iter(rg);
+        unsigned int* cursor = &ha.cursor[h];
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         unsigned long long minr = ~0ull;
         int minfof = -1;
-        for (int row = wid; row < ri.nrows; row += TB / 32) {
-            uint32_t s0, s1;
-            row_span(v, rg, ri, row, s0, s1);
-            for (uint32_t t0 = s0; t0 < s1; t0 += 32) {
-                uint32_t t = t0 + lane;
-                bool in = false;
-                Rec rec;
-                uint32_t fb = 0;
-                if (t < s1) {
-                    double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, v.L, halfL);
-                    if (r2 <= r2max) {
-                        in = true;
-                        Part p = rel_part(v, t, cx, cy, cz, halfL);
-                        rec.rbits = (unsigned long long)__double_as_longlong(p.r);
-                        rec.m = v.mass[t];
-                        uint32_t tc = cfg.dmo ? 1u : (uint32_t)v.type[t];
-                        rec.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u);
-                        if (rec.rbits < minr) { minr = rec.rbits; minfof = v.fof[t]; }
-                        if (nf) fb = fine_bin(p.r, R, nf);
-                    }
-                }
-                if (nf == 0) {
-                    // warp-aggregated append to the halo's single bucket
-                    unsigned bal = __ballot_sync(0xffffffffu, in);
-                    unsigned base = 0;
-                    if (lane == 0 && bal) base = atomicAdd(&s_cursor, (unsigned)__popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (in) out[base + __popc(bal & ((1u << lane) - 1u))] = rec;
-                } else if (in) {
-                    unsigned slot = atomicAdd(&fcur[fb], 1u);
-                    out[(unsigned long long)fex[fb] + slot] = rec;
+        const bool dmo = cfg.dmo != 0;
+        sweep_item<TB>(v, S, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+            bool in = false;
+            Rec rec;
+            uint32_t fb = 0;
+            if (ok) {
+                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+                if (r2 <= r2max) {
+                    in = true;
+                    Part p = rel_part(v, t, cx, cy, cz, halfL);
+                    rec.rbits = (unsigned long long)__double_as_longlong(p.r);
+                    rec.m = v.mass[t];
+                    uint32_t tc = dmo ? 1u : (uint32_t)v.type[t];
+                    rec.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u);
+                    if (rec.rbits < minr) { minr = rec.rbits; minfof = v.fof[t]; }
+                    if (nf) fb = fine_bin(p.r, R, nf);
                 }
             }
-        }
-        // fofid of the innermost particle (SO_properties.py:407-409)
+            if (nf == 0) {
+                // warp-aggregated append to the halo's single bucket
+                unsigned bal = __ballot_sync(0xffffffffu, in);
+                unsigned base = 0;
+                if (lane == 0 && bal) base = atomicAdd(cursor, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) out[base + __popc(bal & ((1u << lane) - 1u))] = rec;
+            } else if (in) {
+                unsigned slot = atomicAdd(&fcur[fb], 1u);
+                out[(unsigned long long)fex[fb] + slot] = rec;
+            }
+        });
+        // fofid of the innermost particle (SO_properties.py:407-409): per-item
+        // minimum, reduced over the halo's items in k_scan_solve
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long orr = __shfl_xor_sync(0xffffffffu, minr, o);
             int of = __shfl_xor_sync(0xffffffffu, minfof, o);
-            if (orr < minr) { minr = orr; minfof = of; }
+            if (orr < minr || (orr == minr && of < minfof)) { minr = orr; minfof = of; }
         }
         if (lane == 0) { s_minr[wid] = minr; s_minfof[wid] = minfof; }
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < TB / 32; w++)
-                if (s_minr[w] < minr) { minr = s_minr[w]; minfof = s_minfof[w]; }
-            ha.sres[h].cen_fof = minfof;
+                if (s_minr[w] < minr || (s_minr[w] == minr && s_minfof[w] < minfof)) { minr = s_minr[w]; minfof = s_minfof[w]; }
+            item_minr[it] = minr;
+            item_minfof[it] = minfof;
         }
+        __syncthreads();
     }
 }
 
@@ -600,7 +639,9 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                                                         const uint32_t* __restrict__ try_list,
                                                         const unsigned int* __restrict__ n_try,
                                                         const Rec* __restrict__ recs,
-                                                        uint32_t* __restrict__ next, Counters* ctr) {
+                                                        uint32_t* __restrict__ next, Counters* ctr,
+                                                        const unsigned long long* __restrict__ item_minr,
+                                                        const int32_t* __restrict__ item_minfof) {
     __shared__ ScanShared<NCH> S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (unsigned int it = blockIdx.x; it < *n_try; it += gridDim.x) {
@@ -834,6 +875,18 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
         __shared__ double s_so_r[SOAP_MAX_SO];
         __shared__ int s_commit_lo, s_commit_hi;
         if (threadIdx.x == 0) {
+            {
+                // innermost particle over the halo's work items (SO_properties.py:407-409)
+                unsigned long long mr = ~0ull;
+                int mf = -1;
+                const uint32_t ib = ha.item_base[h], ni = ha.n_items[h];
+                for (uint32_t k = 0; k < ni; k++)
+                    if (item_minr[ib + k] < mr || (item_minr[ib + k] == mr && item_minfof[ib + k] < mf)) {
+                        mr = item_minr[ib + k];
+                        mf = item_minfof[ib + k];
+                    }
+                sr->cen_fof = mf;
+            }
             int fail = 0;
             double required = 0.0;
             int status = SOAP_HALO_OK;
@@ -1270,6 +1323,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     ha.central = is_central_dev; ha.nexp = nr_bound_part_dev; ha.out = out_dev; ha.ncol = ncol;
     ha.status = status_dev;
     WS_GET(cur_r, double, h, "h_cur_r", H); ha.cur_r = cur_r;
+    WS_GET(rung_r, double, h, "h_rung_r", H); ha.rung_r = rung_r;
     WS_GET(nloop, int32_t, h, "h_nloop", H); ha.nloop = nloop;
     WS_GET(state, int32_t, h, "h_state", H); ha.state = state;
     WS_GET(cnt, uint32_t, h, "h_cnt", H); ha.cnt = cnt;
@@ -1282,12 +1336,22 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(commit_lo, int32_t, h, "h_commit_lo", H); ha.commit_lo = commit_lo;
     WS_GET(commit_hi, int32_t, h, "h_commit_hi", H); ha.commit_hi = commit_hi;
     WS_GET(sres, ScanRes, h, "h_sres", H); ha.sres = sres;
+    WS_GET(item_base, uint32_t, h, "h_item_base", H); ha.item_base = item_base;
+    WS_GET(n_items_arr, uint32_t, h, "h_n_items", H); ha.n_items = n_items_arr;
+    WS_GET(cursor, unsigned int, h, "h_cursor", H); ha.cursor = cursor;
+    WS_GET(items_done, unsigned int, h, "h_items_done", H); ha.items_done = items_done;
+    WS_GET(mslot, int32_t, h, "h_mslot", H); ha.mslot = mslot;
     WS_GET(listA, uint32_t, h, "h_listA", H);
     WS_GET(listB, uint32_t, h, "h_listB", H);
     WS_GET(try_list, uint32_t, h, "h_try", H);
     WS_GET(multi_list, uint32_t, h, "h_multi", H);
     WS_GET(ctr, Counters, h, "h_ctr", 2);
     WS_GET(n_pend_dev, unsigned int, h, "h_npend", 4);
+    // work items: every halo has at least one; large spheres are cut every ITEM_CAND candidates
+    const size_t items_cap = (size_t)H + (size_t)(16 * (v.n / ITEM_CAND + 1)) + 1024;
+    WS_GET(items, Item, h, "h_items", items_cap);
+    WS_GET(item_minr, unsigned long long, h, "h_item_minr", items_cap);
+    WS_GET(item_minfof, int32_t, h, "h_item_minfof", items_cap);
 
     PhaseLog& log = c->halo_log;
     log.reset();
@@ -1306,14 +1370,18 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                                       (int)(SB_CAP * sizeof(Rec))));
         attr_done = true;
     }
+    const unsigned int sweep_grid = (unsigned)(sm * 6);  // persistent CTAs striding over the item list
     unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
     while (n_pend > 0) {
         c->last_rounds++;
         if (c->last_rounds > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
         CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
+        log.begin("plan", stream);
+        LAUNCH(h, k_plan_items, grid_for(n_pend, 128), 128, 0, stream, v, ha, pend, n_pend_dev, items,
+               (unsigned int)items_cap, ctr);
+        log.end(stream);
         log.begin("count", stream);
-        LAUNCH(h, k_count, n_pend < (unsigned)(sm * 32) ? n_pend : (unsigned)(sm * 32), TB, 0, stream, v, ha,
-               pend, n_pend_dev, ctr);
+        LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr);
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list,
@@ -1322,6 +1390,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         Counters hc;
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        if (hc.items_overflow) SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", hc.n_items);
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
@@ -1344,7 +1413,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                 log.begin("fine_hist", stream);
                 CUDA_TRY(cudaMemsetAsync(fine_cnt, 0, sizeof(uint32_t) * (hc.n_fine + 1), stream));
                 CUDA_TRY(cudaMemsetAsync(fine_cur, 0, sizeof(uint32_t) * (hc.n_fine + 1), stream));
-                LAUNCH(h, k_fine_hist_halo, hc.n_multi, TB, 0, stream, v, ha, multi_list, n_multi_dev, fine_cnt);
+                LAUNCH(h, k_fine_hist_halo, sweep_grid, TB, 0, stream, v, ha, items, ctr, fine_cnt);
                 if (soap_exclusive_scan_u32(h, fine_cnt, nullptr, fine_excl, hc.n_fine + 1, nullptr, stream)) return -1;
                 LAUNCH(h, k_build_buckets, grid_for(hc.n_multi, 64), 64, 0, stream, ha, multi_list, n_multi_dev,
                        fine_excl, fine_cnt, 0ull, ctr, bkt_small, bkt_big, bkt_huge);
@@ -1353,8 +1422,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             LAUNCH(h, k_single_buckets, grid_for(n_try, 128), 128, 0, stream, ha, try_list, n_try_dev, ctr,
                    bkt_small, bkt_big);
             log.begin("collect", stream);
-            LAUNCH(h, k_collect, n_try < (unsigned)(sm * 32) ? n_try : (unsigned)(sm * 32), TB, 0, stream, v, ha,
-                   dc, try_list, n_try_dev, fine_excl, fine_cur, ctr, recs);
+            LAUNCH(h, k_collect, sweep_grid, TB, 0, stream, v, ha, dc, items, fine_excl, fine_cur, ctr, recs,
+                   item_minr, item_minfof);
             log.end(stream);
             log.begin("sort", stream);
             {
@@ -1373,13 +1442,15 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             {
                 unsigned int g = n_try < (unsigned)(sm * 8) ? n_try : (unsigned)(sm * 8);
                 if (cfg->dmo)
-                    LAUNCH(h, k_scan_solve<2>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr);
+                    LAUNCH(h, k_scan_solve<2>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr,
+                           item_minr, item_minfof);
                 else
-                    LAUNCH(h, k_scan_solve<8>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr);
+                    LAUNCH(h, k_scan_solve<8>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr,
+                           item_minr, item_minfof);
             }
             log.end(stream);
             log.begin("moments", stream);
-            if (soap_launch_moments(c, dc, ha, try_list, n_try_dev, n_try, stream)) return -1;
+            if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
             log.end(stream);
         }
         // next round's pending list

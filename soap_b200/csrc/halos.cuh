@@ -107,6 +107,7 @@ struct HaloArrays {
     const int32_t* central;
     const int64_t* nexp;
     double* cur_r;
+    double* rung_r;  // radius of the rung being processed (cur_r may already hold the next rung)
     int32_t* nloop;
     int32_t* state;
     int32_t* status;
@@ -122,7 +123,22 @@ struct HaloArrays {
     ScanRes* sres;
     double* out;
     int64_t ncol;
+    // work items of the current rung (sweeps of large halos are split)
+    uint32_t* item_base;
+    uint32_t* n_items;
+    unsigned int* cursor;      // append cursor of single-bucket halos (k_collect)
+    unsigned int* items_done;  // last-arriver counter (k_moments)
+    int32_t* mslot;            // global bank slot of multi-item halos, -1 otherwise
 };
+
+// A work item = a contiguous range [first, first+count) of a halo's candidate
+// stream (its rows concatenated in row order).
+struct Item {
+    uint32_t halo, first, count, pad;
+};
+constexpr uint32_t ITEM_CAND = 32768;  // candidates per item
+constexpr int SWEEP_MAXP = 64;         // row pieces per batch
+constexpr uint32_t LONG_PIECE = 1024;  // longer pieces are swept by the whole CTA
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int range_total(const DimRanges& r) {
@@ -167,5 +183,96 @@ __device__ __forceinline__ void halo_ranges(const ChunkView& v, double cx, doubl
     int d = threadIdx.x;
     double c = d == 0 ? cx : (d == 1 ? cy : cz);
     dim_ranges(c, r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
+}
+
+struct Piece {
+    uint32_t s0, s1;
+};
+struct SweepShared {
+    DimRanges rg[3];
+    Piece pieces[SWEEP_MAXP];
+    int np, row, done;
+    uint32_t pos;
+};
+
+// warp 0: collect the next batch of row pieces of the stream range [a, b)
+__device__ inline void sweep_build_batch(const ChunkView& v, SweepShared& S, const RowIter& ri,
+                                         uint32_t a, uint32_t b) {
+    const int lane = threadIdx.x & 31;
+    int np = 0, row = S.row;
+    uint32_t pos = S.pos;
+    while (row < ri.nrows && pos < b && np < SWEEP_MAXP) {
+        const int r = row + lane;
+        uint32_t s0 = 0, s1 = 0;
+        if (r < ri.nrows) row_span(v, S.rg, ri, r, s0, s1);
+        const uint32_t len = s1 - s0;
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t end = pos + incl, start = end - len;
+        const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
+        const bool has = (r < ri.nrows) && hi > lo;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        const int my = np + __popc(bal & ((1u << lane) - 1u));
+        const int tot = __popc(bal);
+        if (has && my < SWEEP_MAXP) {
+            Piece pc;
+            pc.s0 = s0 + (lo - start);
+            pc.s1 = s0 + (hi - start);
+            S.pieces[my] = pc;
+        }
+        if (np + tot <= SWEEP_MAXP) {
+            np += tot;
+            pos = __shfl_sync(0xffffffffu, end, 31);
+            row += 32;
+        } else {
+            const unsigned lastm = __ballot_sync(0xffffffffu, has && my == SWEEP_MAXP - 1);
+            const int Ln = __ffs(lastm) - 1;
+            np = SWEEP_MAXP;
+            pos = __shfl_sync(0xffffffffu, end, Ln);
+            row += Ln + 1;
+        }
+    }
+    if (lane == 0) {
+        S.np = np;
+        S.row = row;
+        S.pos = pos;
+        S.done = !(row < ri.nrows && pos < b);
+    }
+}
+
+// Sweep the candidates [a, b) of a halo's stream with the whole CTA.  f(t, ok)
+// is called warp-synchronously: every lane of a warp calls it together, ok
+// tells whether t is a real candidate.
+template <int NT, class F>
+__device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx, double cy, double cz,
+                                  double r, uint32_t a, uint32_t b, F f) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, r, S.rg);
+    if (threadIdx.x == 0) { S.row = 0; S.pos = 0; S.done = 0; S.np = 0; }
+    __syncthreads();
+    const RowIter ri = row_iter(S.rg);
+    while (true) {
+        if (wid == 0) sweep_build_batch(v, S, ri, a, b);
+        __syncthreads();
+        const bool done = S.done != 0;
+        const int np = S.np;
+        for (int p = wid; p < np; p += NT / 32) {
+            const Piece pc = S.pieces[p];
+            if (pc.s1 - pc.s0 > LONG_PIECE) continue;
+            for (uint32_t t0 = pc.s0; t0 < pc.s1; t0 += 32) f(t0 + lane, t0 + lane < pc.s1);
+        }
+        for (int p = 0; p < np; p++) {
+            const Piece pc = S.pieces[p];
+            if (pc.s1 - pc.s0 <= LONG_PIECE) continue;
+            for (uint32_t t0 = pc.s0 + wid * 32; t0 < pc.s1; t0 += NT) f(t0 + lane, t0 + lane < pc.s1);
+        }
+        __syncthreads();
+        if (done) break;
+    }
 }
 #endif

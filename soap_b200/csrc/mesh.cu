@@ -264,6 +264,12 @@ int soap_create(int device, soap_handle** out) {
     if (prop.major < 10)
         SOAP_FAIL("soap_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                   device, prop.major, prop.minor);
+    // keep freed pool memory cached (chunks are created and destroyed every step)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
     soap_handle* h = new soap_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;

@@ -189,14 +189,18 @@ __device__ void write_tensor(double* o, const double* s, double n_passed, const 
 
 template <int V, int NTY>
 __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevCfg cfg,
-                                                const uint32_t* __restrict__ try_list,
-                                                const unsigned int* __restrict__ n_try) {
+                                                const Item* __restrict__ items,
+                                                const unsigned int* __restrict__ n_items_dev,
+                                                double* __restrict__ gbanks, int gbank_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* banks = (double*)smem_raw;
-    __shared__ DimRanges rg[3];
+    __shared__ SweepShared SW;
     __shared__ Cuts cuts;
-    for (unsigned int it = blockIdx.x; it < *n_try; it += gridDim.x) {
-        const uint32_t h = try_list[it];
+    __shared__ int s_last;
+    const unsigned int n_items = *n_items_dev;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
         // properties [lo, hi) of halo_prop_list were computed at this rung
         const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
         if (c_hi <= c_lo || ha.status[h] >= 2) continue;
@@ -204,13 +208,12 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
         const bool sub_c = cfg.do_sub && c_lo == 0;
         const ScanRes* sr = ha.sres + h;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
-        const double R = ha.cur_r[h];
-        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L;
+        const double R = ha.rung_r[h];
+        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
         const int32_t hidx = (int32_t)ha.index[h];
         const bool central = ha.central[h] == 1;
         const int n_so = central ? cfg.n_so : 0;
         __syncthreads();
-        if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, R, rg);
         if (threadIdx.x == 32) {
             Cuts& c = cuts;
             c.n = 0;
@@ -232,65 +235,76 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
         const int nbank = (ncut + 1) * 2 * NTY;
         for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = 0.0;
         __syncthreads();
-        const RowIter ri = row_iter(rg);
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         const int32_t cen_fof = sr->cen_fof;
         Acc<V> acc;
         acc.key = -1;
         acc.clear();
-        for (int row = wid; row < ri.nrows; row += TB / 32) {
-            uint32_t s0, s1;
-            row_span(v, rg, ri, row, s0, s1);
-            for (uint32_t t = s0 + lane; t < s1; t += 32) {
-                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, v.L, halfL);
-                if (!(r2 <= r2max)) continue;
-                const double x = rewrap_rel(v.px[t], cx, v.L, halfL);
-                const double y = rewrap_rel(v.py[t], cy, v.L, halfL);
-                const double z = rewrap_rel(v.pz[t], cz, v.L, halfL);
-                const double r = radius3(x, y, z);
-                int shell = 0;
-                for (int k = 0; k < ncut; k++) shell += cuts.strict[k] ? !(r < cuts.r[k]) : !(r <= cuts.r[k]);
-                const int32_t g = v.grnr[t];
-                const int bound = g == hidx;
-                const uint32_t tc = NTY == 1 ? 1u : (uint32_t)v.type[t];
-                const int key = (shell * 2 + bound) * NTY + (NTY == 1 ? 0 : (int)tc);
-                if (key != acc.key) { acc.flush(banks); acc.key = key; }
-                const double m = (double)v.mass[t];
-                const double vx = (double)v.vx[t], vy = (double)v.vy[t], vz = (double)v.vz[t];
-                acc.v[V_N] += 1.0;
-                acc.v[V_M] += m;
-                acc.v[V_MX] += m * x; acc.v[V_MX + 1] += m * y; acc.v[V_MX + 2] += m * z;
-                acc.v[V_MV] += m * vx; acc.v[V_MV + 1] += m * vy; acc.v[V_MV + 2] += m * vz;
-                acc.v[V_ML] += m * (y * vz - z * vy);
-                acc.v[V_ML + 1] += m * (z * vx - x * vz);
-                acc.v[V_ML + 2] += m * (x * vy - y * vx);
-                acc.v[V_MR] += m * r;
-                acc.v[V_MRS] += m * fmax(cfg.soft[tc], r);
-                if (!bound && g >= 0) {
-                    // SO_properties.py:461-466
-                    if (v.fof[t] == cen_fof) acc.v[V_SAT] += m; else acc.v[V_EXT] += m;
-                }
-                if constexpr (V >= V_FULL) {
-                    acc.v[V_VV] += m * vx * vx; acc.v[V_VV + 1] += m * vy * vy; acc.v[V_VV + 2] += m * vz * vz;
-                    acc.v[V_VV + 3] += m * vx * vy; acc.v[V_VV + 4] += m * vx * vz; acc.v[V_VV + 5] += m * vy * vz;
-                    acc.v[V_XV] += m * (x * vx + y * vy + z * vz);
-                    const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
-                    acc.v[V_XX] += m * xx; acc.v[V_XX + 1] += m * yy; acc.v[V_XX + 2] += m * zz;
-                    acc.v[V_XX + 3] += m * xy; acc.v[V_XX + 4] += m * xz; acc.v[V_XX + 5] += m * yz;
-                    const double nrm = r * r;
-                    if (nrm <= 1e-8) {  // np.isclose(norm, 0): inertia_tensors.py:62-64
-                        acc.v[V_M0] += m; acc.v[V_N0] += 1.0;
-                    } else {
-                        const double w = m / nrm;
-                        acc.v[V_XXR] += w * xx; acc.v[V_XXR + 1] += w * yy; acc.v[V_XXR + 2] += w * zz;
-                        acc.v[V_XXR + 3] += w * xy; acc.v[V_XXR + 4] += w * xz; acc.v[V_XXR + 5] += w * yz;
-                    }
+        sweep_item<TB>(v, SW, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+            if (!ok) return;
+            double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+            if (!(r2 <= r2max)) return;
+            const double x = rewrap_rel(v.px[t], cx, L, halfL);
+            const double y = rewrap_rel(v.py[t], cy, L, halfL);
+            const double z = rewrap_rel(v.pz[t], cz, L, halfL);
+            const double r = radius3(x, y, z);
+            int shell = 0;
+            for (int k = 0; k < ncut; k++) shell += cuts.strict[k] ? !(r < cuts.r[k]) : !(r <= cuts.r[k]);
+            const int32_t g = v.grnr[t];
+            const int bound = g == hidx;
+            const uint32_t tc = NTY == 1 ? 1u : (uint32_t)v.type[t];
+            const int key = (shell * 2 + bound) * NTY + (NTY == 1 ? 0 : (int)tc);
+            if (key != acc.key) { acc.flush(banks); acc.key = key; }
+            const double m = (double)v.mass[t];
+            const double vx = (double)v.vx[t], vy = (double)v.vy[t], vz = (double)v.vz[t];
+            acc.v[V_N] += 1.0;
+            acc.v[V_M] += m;
+            acc.v[V_MX] += m * x; acc.v[V_MX + 1] += m * y; acc.v[V_MX + 2] += m * z;
+            acc.v[V_MV] += m * vx; acc.v[V_MV + 1] += m * vy; acc.v[V_MV + 2] += m * vz;
+            acc.v[V_ML] += m * (y * vz - z * vy);
+            acc.v[V_ML + 1] += m * (z * vx - x * vz);
+            acc.v[V_ML + 2] += m * (x * vy - y * vx);
+            acc.v[V_MR] += m * r;
+            acc.v[V_MRS] += m * fmax(cfg.soft[tc], r);
+            if (!bound && g >= 0) {
+                // SO_properties.py:461-466
+                if (v.fof[t] == cen_fof) acc.v[V_SAT] += m; else acc.v[V_EXT] += m;
+            }
+            if constexpr (V >= V_FULL) {
+                acc.v[V_VV] += m * vx * vx; acc.v[V_VV + 1] += m * vy * vy; acc.v[V_VV + 2] += m * vz * vz;
+                acc.v[V_VV + 3] += m * vx * vy; acc.v[V_VV + 4] += m * vx * vz; acc.v[V_VV + 5] += m * vy * vz;
+                acc.v[V_XV] += m * (x * vx + y * vy + z * vz);
+                const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+                acc.v[V_XX] += m * xx; acc.v[V_XX + 1] += m * yy; acc.v[V_XX + 2] += m * zz;
+                acc.v[V_XX + 3] += m * xy; acc.v[V_XX + 4] += m * xz; acc.v[V_XX + 5] += m * yz;
+                const double nrm = r * r;
+                if (nrm <= 1e-8) {  // np.isclose(norm, 0): inertia_tensors.py:62-64
+                    acc.v[V_M0] += m; acc.v[V_N0] += 1.0;
+                } else {
+                    const double w = m / nrm;
+                    acc.v[V_XXR] += w * xx; acc.v[V_XXR + 1] += w * yy; acc.v[V_XXR + 2] += w * zz;
+                    acc.v[V_XXR + 3] += w * xy; acc.v[V_XXR + 4] += w * xz; acc.v[V_XXR + 5] += w * yz;
                 }
             }
-        }
+        });
         acc.flush(banks);
         acc.key = -1;
         __syncthreads();
+        // halos swept by several work items: combine in global banks; the last
+        // item to arrive writes the result row
+        const uint32_t n_it = ha.n_items[h];
+        if (n_it > 1) {
+            double* gb = gbanks + (size_t)ha.mslot[h] * gbank_stride;
+            for (int i = threadIdx.x; i < nbank * V; i += TB)
+                if (banks[i] != 0.0) atomicAdd(&gb[i], banks[i]);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(&ha.items_done[h], 1u) == n_it - 1) ? 1 : 0;
+            __syncthreads();
+            if (!s_last) continue;
+            __threadfence();
+            for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = __ldcg(&gb[i]);
+            __syncthreads();
+        }
         // ------------------------------------------------------- result row
         // one thread per selection: 0 = subhalo, 1.. = SO, then apertures
         const int nsel = 1 + SOAP_MAX_SO + SOAP_MAX_APERTURES;
@@ -419,20 +433,26 @@ __global__ void k_write_input_cols(HaloArrays ha, int64_t nh) {
 
 }  // namespace
 
-int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha,
-                        const uint32_t* try_list, const uint32_t* n_try_dev, uint32_t n_try_host,
-                        cudaStream_t stream) {
+int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
+                        const unsigned int* n_items_dev, unsigned int n_items_host,
+                        unsigned int n_mslot, unsigned int grid, cudaStream_t stream) {
     soap_handle* h = c->h;
     const bool full = (cfg.flags & (PF_KIN | PF_KAPPA | PF_TENS)) != 0;
     const int nty = cfg.dmo ? 1 : 4;
     const int V = full ? V_FULL : V_MIN;
-    const size_t smem = (size_t)(cfg.n_so + cfg.n_ap + 3) * 2 * nty * V * sizeof(double);
-    unsigned int g = n_try_host < (unsigned)(h->sm_count * 16) ? n_try_host : (unsigned)(h->sm_count * 16);
+    const int stride = (cfg.n_so + cfg.n_ap + 3) * 2 * nty * V;
+    const size_t smem = (size_t)stride * sizeof(double);
+    double* gbanks = (double*)h->get("h_gbanks", sizeof(double) * (size_t)stride * (n_mslot + 1));
+    if (!gbanks) return -1;
+    if (n_mslot > 0) CUDA_TRY(cudaMemsetAsync(gbanks, 0, sizeof(double) * (size_t)stride * n_mslot, stream));
+    unsigned int g = n_items_host < grid ? n_items_host : grid;
+    if (g < 1) g = 1;
 #define MOM(VV, NT)                                                                                   \
     do {                                                                                              \
         CUDA_TRY(cudaFuncSetAttribute(k_moments<VV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)smem));                                                    \
-        LAUNCH(h, (k_moments<VV, NT>), g, TB, smem, stream, c->v, ha, cfg, try_list, n_try_dev);      \
+        LAUNCH(h, (k_moments<VV, NT>), g, TB, smem, stream, c->v, ha, cfg, items, n_items_dev, gbanks, \
+               stride);                                                                               \
     } while (0)
     if (full && nty == 4) MOM(V_FULL, 4);
     else if (full) MOM(V_FULL, 1);
