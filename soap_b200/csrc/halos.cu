@@ -18,6 +18,9 @@
 //   k_moments      (moments.cu) masked moment sums + result row
 #include "halos.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
                         const unsigned int* n_items_dev, unsigned int n_items_host,
                         unsigned int n_mslot, unsigned int grid, cudaStream_t stream);
@@ -25,10 +28,12 @@ int soap_write_input_cols(soap_handle* h, const HaloArrays& ha, int64_t nh, cuda
 
 namespace {
 
-constexpr int TB = 256;
+constexpr int TB = SWEEP_NT;
 constexpr int SB_CAP = 4096;     // records of one bucket sorted in shared memory (64 KB)
 constexpr int SMALL_CAP = 512;   // small-bucket class (8 KB)
 constexpr int FINE_TARGET = 128; // expected records per fine radial bin
+constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
+constexpr int SCAN_CS = 8;            // CTAs per cluster for those
 
 struct Bucket {
     unsigned long long start;
@@ -38,7 +43,7 @@ struct Bucket {
 
 // device counters of one round
 struct Counters {
-    unsigned int n_try, n_next, n_multi, n_fine;
+    unsigned int n_try, n_big, n_next, n_multi, n_fine;
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
     unsigned int n_mslot, items_overflow;
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
     if (ni < 1) ni = 1;
     uint32_t base = atomicAdd(&ctr->n_items, ni);
     if (base + ni > items_cap) {
+        // the host grows the item list to n_items and plans this rung again
         atomicExch(&ctr->items_overflow, 1u);
-        ni = base < items_cap ? 1u : 0u;  // degrade: a single item covers the whole stream
+        return;
     }
     ha.item_base[h] = base;
     ha.n_items[h] = ni;
@@ -100,13 +106,33 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
     ha.items_done[h] = 0;
     ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
     ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
-    for (uint32_t k = 0; k < ni; k++) {
+    if (ni == 1) {
         Item im;
-        im.halo = h;
-        im.first = k * ITEM_CAND;
-        im.count = (ni == 1) ? (uint32_t)cand : (uint32_t)((cand - (unsigned long long)k * ITEM_CAND) < ITEM_CAND ? (cand - (unsigned long long)k * ITEM_CAND) : ITEM_CAND);
-        im.pad = k;
-        items[base + k] = im;
+        im.halo = h; im.first = 0; im.count = (uint32_t)cand; im.row0 = 0;
+        im.pos0 = 0; im.k = 0; im.pad0 = im.pad1 = 0;
+        items[base] = im;
+    } else {
+        // second walk: the row in which each item's range starts
+        unsigned long long pos = 0;
+        uint32_t k = 0;
+        for (int row = 0; row < ri.nrows && k < ni; row++) {
+            uint32_t s0, s1;
+            row_span(v, rg, ri, row, s0, s1);
+            const unsigned long long end = pos + (s1 - s0);
+            while (k < ni && (unsigned long long)k * ITEM_CAND < end) {
+                Item im;
+                im.halo = h;
+                im.first = k * ITEM_CAND;
+                const unsigned long long left = cand - (unsigned long long)k * ITEM_CAND;
+                im.count = (uint32_t)(left < ITEM_CAND ? left : ITEM_CAND);
+                im.row0 = (uint32_t)row;
+                im.pos0 = (uint32_t)pos;
+                im.k = k; im.pad0 = im.pad1 = 0;
+                items[base + k] = im;
+                k++;
+            }
+            pos = end;
+        }
     }
     atomicAdd(&ctr->candidates, cand);
 }
@@ -129,7 +155,7 @@ __global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const 
         const double halfL = 0.5 * v.L, L = v.L;
         unsigned long long cnt = 0;
         double msum = 0.0;
-        sweep_item<TB>(v, S, cx, cy, cz, r, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+        sweep_item(v, S, cx, cy, cz, r, im, [&](uint32_t t, bool ok) {
             if (ok) {
                 double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
                 if (r2 <= r2max) {
@@ -179,6 +205,7 @@ __device__ inline bool ladder_step(const HaloArrays& ha, uint32_t h, double requ
 __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ pend,
                                               const unsigned int* __restrict__ n_pend,
                                               uint32_t* __restrict__ try_list,
+                                              uint32_t* __restrict__ big_list,
                                               uint32_t* __restrict__ multi_list,
                                               uint32_t* __restrict__ next, Counters* ctr) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,10 +217,10 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
     const double density = ha.msum[h] / (4.0 / 3.0 * SOAP_PI * (r * r * r));
     const bool has_target = ha.central[h] == 1 && cfg.target_density > 0.0;  // halo_tasks.py:381
     if (!has_target || density <= cfg.target_density) {  // halo_tasks.py:103
-        unsigned int slot = atomicAdd(&ctr->n_try, 1u);
-        try_list[slot] = h;
-        ha.state[h] = ST_TRY;
         const uint32_t cnt = ha.cnt[h];
+        if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // scanned by a CTA cluster
+        else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
+        ha.state[h] = ST_TRY;
         if (cnt <= SB_CAP) {
             ha.rec_off[h] = atomicAdd(&ctr->rec_single, (unsigned long long)cnt);
             ha.nfine[h] = 0;
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays h
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
         const uint32_t nf = ha.nfine[h];
         uint32_t* fc = fine_cnt + ha.fine_off[h];
-        sweep_item<TB>(v, S, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+        sweep_item(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             if (ok) {
                 double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
                 if (r2 <= r2max) {
@@ -257,38 +284,39 @@ __global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays h
     }
 }
 
-// Greedy grouping of a multi-bucket halo's fine bins into sort buckets of at
-// most SB_CAP records (one thread per halo; few such halos).
-__global__ void k_build_buckets(HaloArrays ha, const uint32_t* __restrict__ multi_list,
-                                const unsigned int* __restrict__ n_multi,
-                                const int64_t* __restrict__ fine_excl, const uint32_t* __restrict__ fine_cnt,
-                                unsigned long long multi_base_unused, Counters* ctr,
-                                Bucket* __restrict__ bkt_small, Bucket* __restrict__ bkt_big,
-                                Bucket* __restrict__ bkt_huge) {
-    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= *n_multi) return;
-    const uint32_t h = multi_list[it];
+// Group a multi-bucket halo's fine radial bins into sort buckets: bins whose
+// first record falls into the same BKT_SPAN-wide window of the halo's record
+// range form one bucket (one CTA per halo, one thread per bin; a bin starts a
+// bucket if its window differs from its predecessor's).  A bucket holds at
+// most BKT_SPAN - 1 records plus its last bin.
+constexpr uint32_t BKT_SPAN = SB_CAP / 2;
+__global__ void __launch_bounds__(256) k_build_buckets(HaloArrays ha, const uint32_t* __restrict__ multi_list,
+                                                       const int64_t* __restrict__ fine_excl, Counters* ctr,
+                                                       Bucket* __restrict__ bkt_small, Bucket* __restrict__ bkt_big,
+                                                       Bucket* __restrict__ bkt_huge) {
+    const uint32_t h = multi_list[blockIdx.x];
     const uint32_t nf = ha.nfine[h], fo = ha.fine_off[h];
     const unsigned long long base = ctr->rec_single;  // multi region follows the single region
-    ha.rec_off[h] = base + (unsigned long long)fine_excl[fo];
-    unsigned long long cur_start = (unsigned long long)fine_excl[fo];
-    uint32_t cur_cnt = 0;
-    for (uint32_t f = 0; f <= nf; f++) {
-        uint32_t c = f < nf ? fine_cnt[fo + f] : 0u;
-        if (f == nf || (cur_cnt > 0 && cur_cnt + c > SB_CAP)) {
-            if (cur_cnt > 0) {
-                Bucket b;
-                b.start = base + cur_start;
-                b.count = cur_cnt;
-                b.halo = h;
-                if (cur_cnt <= SMALL_CAP) bkt_small[atomicAdd(&ctr->n_bkt_small, 1u)] = b;
-                else if (cur_cnt <= SB_CAP) bkt_big[atomicAdd(&ctr->n_bkt_big, 1u)] = b;
-                else bkt_huge[atomicAdd(&ctr->n_bkt_huge, 1u)] = b;
-            }
-            cur_start += cur_cnt;
-            cur_cnt = 0;
-        }
-        cur_cnt += c;
+    const unsigned long long e0 = (unsigned long long)fine_excl[fo];
+    if (threadIdx.x == 0) ha.rec_off[h] = base + e0;
+    const unsigned long long e_end = e0 + ha.cnt[h];
+    for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x) {
+        const unsigned long long ef = (unsigned long long)fine_excl[fo + f];
+        const unsigned long long gf = (ef - e0) / BKT_SPAN;
+        if (f > 0 && ((unsigned long long)fine_excl[fo + f - 1] - e0) / BKT_SPAN == gf) continue;
+        // bucket start: find the first later bin in another window
+        uint32_t f2 = f + 1;
+        while (f2 < nf && ((unsigned long long)fine_excl[fo + f2] - e0) / BKT_SPAN == gf) f2++;
+        const unsigned long long e2 = f2 < nf ? (unsigned long long)fine_excl[fo + f2] : e_end;
+        const unsigned long long c = e2 - ef;
+        if (c == 0) continue;
+        Bucket b;
+        b.start = base + ef;
+        b.count = (uint32_t)c;
+        b.halo = h;
+        if (c <= SMALL_CAP) bkt_small[atomicAdd(&ctr->n_bkt_small, 1u)] = b;
+        else if (c <= SB_CAP) bkt_big[atomicAdd(&ctr->n_bkt_big, 1u)] = b;
+        else bkt_huge[atomicAdd(&ctr->n_bkt_huge, 1u)] = b;
     }
 }
 
@@ -339,7 +367,7 @@ __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevC
         unsigned long long minr = ~0ull;
         int minfof = -1;
         const bool dmo = cfg.dmo != 0;
-        sweep_item<TB>(v, S, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
+        sweep_item(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             bool in = false;
             Rec rec;
             uint32_t fb = 0;
@@ -419,6 +447,17 @@ constexpr int SCAN_K = 4;
 constexpr int SCAN_TILE = SCAN_NT * SCAN_K;
 constexpr uint32_t NONE = 0xffffffffu;
 
+// first-index targets of the scan passes
+enum {
+    T_SO = 0,                                    // first record at or below each SO density
+    T_NONNEG = T_SO + SOAP_MAX_SO,               // first non-negative cumulative mass
+    T_SUBHMR = T_NONNEG + 1,                     // bound half-mass crossings (tot, gas, dm, star, baryon)
+    T_APEDGE = T_SUBHMR + 5,                     // first record beyond each aperture
+    T_APHMR = T_APEDGE + SOAP_MAX_APERTURES,     // aperture half-mass crossings [a][g]
+    T_DMOUT = T_APHMR + 4 * SOAP_MAX_APERTURES,  // first dark matter particle outside each SO
+    T_COUNT = T_DMOUT + SOAP_MAX_SO
+};
+
 template <int NCH>
 struct ScanShared {
     double carry[NCH];
@@ -429,16 +468,25 @@ struct ScanShared {
     double tot[NCH], rmaxc[NCH];
     uint32_t cnt[NCH], cnt0[NCH];
     uint32_t n_zero;
-    // first-index targets
-    uint32_t so_idx[SOAP_MAX_SO], nonneg_idx, sub_hmr_idx[5], ap_edge_idx[SOAP_MAX_APERTURES],
-        ap_hmr_idx[SOAP_MAX_APERTURES][4], dm_out_idx[SOAP_MAX_SO];
-    // captures
-    double so_cap[SOAP_MAX_SO][3];      // r_i, cumall_incl, cumall_excl
-    double nonneg_cap[2];               // r, cm32
-    double sub_hmr_cap[5][3];           // r_i, W_incl, W_excl
-    double ap_edge_cap[SOAP_MAX_APERTURES][NCH];
-    double ap_hmr_cap[SOAP_MAX_APERTURES][4][3];
-    double dm_out_cap[SOAP_MAX_SO][2];  // r2, m2
+    // first-index targets (T_*) and the values captured at them
+    uint32_t tidx[T_COUNT];
+    double tcap[T_COUNT][NCH < 3 ? 3 : NCH];
+    // cluster merge scratch (rank 0)
+    uint32_t m_idx[T_COUNT];
+    uint8_t m_owner[T_COUNT];
+    // local (this CTA's tile range) pass A results; tot/cnt/... above are the halo's
+    double l_tot[NCH], l_rmaxc[NCH];
+    uint32_t l_cnt[NCH], l_cnt0[NCH], l_n_zero;
+    double carry_in[NCH];
+    uint32_t carryc_in[NCH];
+    // published block argmax results: 0 unsoftened, 1 softened subhalo Vmax, 2.. SO Vmax
+    double pub_v[2 + SOAP_MAX_SO], pub_r[2 + SOAP_MAX_SO];
+    uint32_t pub_i[2 + SOAP_MAX_SO];
+    // outcome of the solve (rank 0), read by the other CTAs of the cluster
+    int fail_;  // 0 ok, 1 retry, >=2 fatal status
+    double required_;
+    double so_r_[SOAP_MAX_SO];
+    int commit_lo_, commit_hi_;
     double ap_thr[SOAP_MAX_APERTURES][4];
     // argmax block reduce
     double am_v[SCAN_NT / 32], am_r[SCAN_NT / 32];
@@ -632,19 +680,50 @@ __device__ inline void argmax_reduce(ArgMax& a, ScanShared<NCH>& S) {
     __syncthreads();
 }
 
-// One CTA per halo of the try list.  Three streaming passes over the halo's
-// radially sorted records.
-template <int NCH>
-__global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cfg,
-                                                        const uint32_t* __restrict__ try_list,
-                                                        const unsigned int* __restrict__ n_try,
-                                                        const Rec* __restrict__ recs,
-                                                        uint32_t* __restrict__ next, Counters* ctr,
-                                                        const unsigned long long* __restrict__ item_minr,
-                                                        const int32_t* __restrict__ item_minfof) {
+// One CTA (CS == 1) or one cluster of CS CTAs (halos above SCAN_BIG records) per
+// halo of the list.  Three streaming passes over the halo's radially sorted
+// records.  In a cluster every CTA owns a contiguous range of tiles: pass A
+// totals give each CTA its carry-in, the first-index targets and argmax
+// candidates found locally in passes B and C are merged by rank 0 through
+// distributed shared memory, and rank 0 alone runs the solve.
+template <int NCH, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT)
+    k_scan_solve(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ try_list,
+                 const unsigned int* __restrict__ n_try, const Rec* __restrict__ recs,
+                 uint32_t* __restrict__ next, Counters* ctr,
+                 const unsigned long long* __restrict__ item_minr,
+                 const int32_t* __restrict__ item_minfof) {
     __shared__ ScanShared<NCH> S;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int crank = CS > 1 ? cluster.block_rank() : 0u;
+    const unsigned int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
+    auto csync = [&]() { if (CS > 1) cluster.sync(); else __syncthreads(); };
+    auto peer = [&](unsigned int rk) -> ScanShared<NCH>* { return CS > 1 ? cluster.map_shared_rank(&S, rk) : &S; };
+    // rank 0: merge the first-index targets found by the other CTAs into S
+    auto merge_targets = [&]() {
+        if (CS > 1 && crank == 0) {
+            constexpr int CW = NCH < 3 ? 3 : NCH;
+            for (int j = threadIdx.x; j < T_COUNT; j += SCAN_NT) {
+                uint32_t best = S.tidx[j];
+                unsigned int owner = 0;
+                for (unsigned int rk = 1; rk < CS; rk++) {
+                    const uint32_t o = peer(rk)->tidx[j];
+                    if (o < best) { best = o; owner = rk; }
+                }
+                S.m_idx[j] = best;
+                S.m_owner[j] = (uint8_t)owner;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < T_COUNT * CW; e += SCAN_NT) {
+                const int j = e / CW, k = e % CW;
+                if (S.m_owner[j]) S.tcap[j][k] = peer(S.m_owner[j])->tcap[j][k];
+            }
+            for (int j = threadIdx.x; j < T_COUNT; j += SCAN_NT) S.tidx[j] = S.m_idx[j];
+            __syncthreads();
+        }
+    };
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (unsigned int it = blockIdx.x; it < *n_try; it += gridDim.x) {
+    for (unsigned int it = cid; it < *n_try; it += ncl) {
         const uint32_t h = try_list[it];
         const uint32_t n = ha.cnt[h];
         const Rec* R = recs + ha.rec_off[h];
@@ -653,20 +732,27 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
         const int n_so = central ? cfg.n_so : 0;  // SO_properties.py:3627
         const int n_ap = cfg.n_ap;
         const bool want_hmr = (cfg.flags & PF_HMR) != 0;
+        // this CTA's tiles
+        const uint32_t ntile = (n + SCAN_TILE - 1) / SCAN_TILE;
+        const uint32_t tiles_per = (ntile + CS - 1) / CS;
+        const uint32_t t_lo = crank * tiles_per < ntile ? crank * tiles_per : ntile;
+        const uint32_t t_hi = t_lo + tiles_per < ntile ? t_lo + tiles_per : ntile;
+        const uint32_t i_lo = t_lo * SCAN_TILE;
+        const uint32_t i_hi = (unsigned long long)t_hi * SCAN_TILE < n ? t_hi * SCAN_TILE : n;
         __syncthreads();
         // ------------------------------------------------------------ pass A
         if (threadIdx.x < NCH) {
-            S.tot[threadIdx.x] = 0.0; S.rmaxc[threadIdx.x] = 0.0;
-            S.cnt[threadIdx.x] = 0; S.cnt0[threadIdx.x] = 0;
+            S.l_tot[threadIdx.x] = 0.0; S.l_rmaxc[threadIdx.x] = 0.0;
+            S.l_cnt[threadIdx.x] = 0; S.l_cnt0[threadIdx.x] = 0;
         }
-        if (threadIdx.x == 0) S.n_zero = 0;
+        if (threadIdx.x == 0) S.l_n_zero = 0;
         __syncthreads();
         {
             double tot[NCH], rmx[NCH];
             uint32_t cnt[NCH], cnt0[NCH], nz = 0;
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) { tot[ch] = 0.0; rmx[ch] = 0.0; cnt[ch] = 0; cnt0[ch] = 0; }
-            for (uint32_t i = threadIdx.x; i < n; i += SCAN_NT) {
+            for (uint32_t i = i_lo + threadIdx.x; i < i_hi; i += SCAN_NT) {
                 Rec rc = R[i];
                 double r = __longlong_as_double((long long)rc.rbits);
                 int c = rec_class<NCH>(rc.flags);
@@ -687,15 +773,37 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                 uint32_t a = (uint32_t)warp_sum_u64(cnt[ch]);
                 uint32_t b = (uint32_t)warp_sum_u64(cnt0[ch]);
                 if (lane == 0) {
-                    atomicAdd(&S.tot[ch], t);
-                    atomicAdd(&S.cnt[ch], a);
-                    atomicAdd(&S.cnt0[ch], b);
+                    atomicAdd(&S.l_tot[ch], t);
+                    atomicAdd(&S.l_cnt[ch], a);
+                    atomicAdd(&S.l_cnt0[ch], b);
                     // non-negative doubles order like their bit patterns
-                    atomicMax((unsigned long long*)&S.rmaxc[ch], (unsigned long long)__double_as_longlong(m));
+                    atomicMax((unsigned long long*)&S.l_rmaxc[ch], (unsigned long long)__double_as_longlong(m));
                 }
             }
             nz = (uint32_t)warp_sum_u64(nz);
-            if (lane == 0) atomicAdd(&S.n_zero, nz);
+            if (lane == 0) atomicAdd(&S.l_n_zero, nz);
+        }
+        csync();
+        // halo totals and this CTA's carry-in (sum over the lower ranks)
+        if (threadIdx.x < NCH) {
+            const int ch = threadIdx.x;
+            double tot = 0.0, rmx = 0.0, cin = 0.0;
+            uint32_t cnt = 0, cnt0 = 0, ccin = 0;
+            for (unsigned int rk = 0; rk < CS; rk++) {
+                const ScanShared<NCH>* P = peer(rk);
+                const double t = P->l_tot[ch];
+                const uint32_t c = P->l_cnt[ch];
+                if (rk < crank) { cin += t; ccin += c; }
+                tot += t; cnt += c; cnt0 += P->l_cnt0[ch];
+                rmx = fmax(rmx, P->l_rmaxc[ch]);
+            }
+            S.tot[ch] = tot; S.cnt[ch] = cnt; S.cnt0[ch] = cnt0; S.rmaxc[ch] = rmx;
+            S.carry_in[ch] = cin; S.carryc_in[ch] = ccin;
+        }
+        if (threadIdx.x == NCH) {
+            uint32_t nz = 0;
+            for (unsigned int rk = 0; rk < CS; rk++) nz += peer(rk)->l_n_zero;
+            S.n_zero = nz;
         }
         __syncthreads();
         // bound totals
@@ -723,20 +831,13 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
         const uint32_t nskip_s = (min_soft <= 1e-8) ? fnc_u : 0u;
 
         // ------------------------------------------------------------ pass B
-        if (threadIdx.x < NCH) { S.carry[threadIdx.x] = 0.0; S.carryc[threadIdx.x] = 0; }
-        if (threadIdx.x < SOAP_MAX_SO) { S.so_idx[threadIdx.x] = NONE; S.dm_out_idx[threadIdx.x] = NONE; }
-        if (threadIdx.x < 5) S.sub_hmr_idx[threadIdx.x] = NONE;
-        if (threadIdx.x < SOAP_MAX_APERTURES) {
-            S.ap_edge_idx[threadIdx.x] = NONE;
-            for (int g = 0; g < 4; g++) S.ap_hmr_idx[threadIdx.x][g] = NONE;
-        }
-        if (threadIdx.x == 0) S.nonneg_idx = NONE;
+        if (threadIdx.x < NCH) { S.carry[threadIdx.x] = S.carry_in[threadIdx.x]; S.carryc[threadIdx.x] = S.carryc_in[threadIdx.x]; }
+        for (int j = threadIdx.x; j < T_COUNT; j += SCAN_NT) S.tidx[j] = NONE;
         __syncthreads();
         ArgMax amU, amS;
         amU.init();
         amS.init();
-        const uint32_t ntile = (n + SCAN_TILE - 1) / SCAN_TILE;
-        for (uint32_t tile = 0; tile < ntile; tile++) {
+        for (uint32_t tile = t_lo; tile < t_hi; tile++) {
             const uint32_t i0 = tile * SCAN_TILE + threadIdx.x * SCAN_K;
             Rec rc[SCAN_K];
             double base[NCH];
@@ -782,8 +883,8 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     float cm = so_cm32(call_in, r, cfg.nu);
                     double dens = so_density(cm, r);
                     for (int q = 0; q < n_so; q++)
-                        if (!(dens > cfg.so_rho[q]) && i < S.so_idx[q]) atomicMin(&S.so_idx[q], i);
-                    if (!(cm < 0.f) && i < S.nonneg_idx) atomicMin(&S.nonneg_idx, i);
+                        if (!(dens > cfg.so_rho[q]) && i < S.tidx[T_SO + (q)]) atomicMin(&S.tidx[T_SO + (q)], i);
+                    if (!(cm < 0.f) && i < S.tidx[T_NONNEG]) atomicMin(&S.tidx[T_NONNEG], i);
                 }
                 if (bound) {
                     const double cb_in = cb_ex + m;
@@ -794,22 +895,22 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                         if (posb >= nskip_s && rs > 0.0) amS.offer(cb_in / rs, rs, i);
                         // half-mass radii (half_mass_radius.py:63)
                         if (want_hmr || true) {
-                            if (cb_in >= 0.5 * Mb_g[0] && i < S.sub_hmr_idx[0]) atomicMin(&S.sub_hmr_idx[0], i);
+                            if (cb_in >= 0.5 * Mb_g[0] && i < S.tidx[T_SUBHMR + (0)]) atomicMin(&S.tidx[T_SUBHMR + (0)], i);
                         }
                         if (want_hmr) {
 #pragma unroll
                             for (int g = 0; g < 4; g++)
                                 if (in_group(g, tc)) {
                                     double w = group_sum<NCH>(base, g, true);
-                                    if (w >= 0.5 * Mb_g[1 + g] && i < S.sub_hmr_idx[1 + g])
-                                        atomicMin(&S.sub_hmr_idx[1 + g], i);
+                                    if (w >= 0.5 * Mb_g[1 + g] && i < S.tidx[T_SUBHMR + (1 + g)])
+                                        atomicMin(&S.tidx[T_SUBHMR + (1 + g)], i);
                                 }
                         }
                     }
                 }
                 // first record beyond each aperture radius (aperture_properties.py:310)
                 for (int a = 0; a < n_ap; a++)
-                    if (want_hmr && r > cfg.ap_r[a] && i < S.ap_edge_idx[a]) atomicMin(&S.ap_edge_idx[a], i);
+                    if (want_hmr && r > cfg.ap_r[a] && i < S.tidx[T_APEDGE + (a)]) atomicMin(&S.tidx[T_APEDGE + (a)], i);
             }
             __syncthreads();
             // capture sweep: the owner of a newly found index re-derives its values
@@ -833,31 +934,31 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     for (int ch = 0; ch < NCH; ch++)
                         if (c == ch) bb[ch] += m;
                     for (int q = 0; q < n_so; q++)
-                        if (S.so_idx[q] == i) {
-                            S.so_cap[q][0] = r; S.so_cap[q][1] = call_ex + m; S.so_cap[q][2] = call_ex;
+                        if (S.tidx[T_SO + (q)] == i) {
+                            S.tcap[T_SO + (q)][0] = r; S.tcap[T_SO + (q)][1] = call_ex + m; S.tcap[T_SO + (q)][2] = call_ex;
                         }
-                    if (S.nonneg_idx == i) {
-                        S.nonneg_cap[0] = r;
-                        S.nonneg_cap[1] = (double)so_cm32(call_ex + m, r, cfg.nu);
+                    if (S.tidx[T_NONNEG] == i) {
+                        S.tcap[T_NONNEG][0] = r;
+                        S.tcap[T_NONNEG][1] = (double)so_cm32(call_ex + m, r, cfg.nu);
                     }
                     if (cfg.do_sub) {
-                        if (S.sub_hmr_idx[0] == i) {
-                            S.sub_hmr_cap[0][0] = r;
-                            S.sub_hmr_cap[0][1] = bound_sum<NCH>(bb);
-                            S.sub_hmr_cap[0][2] = bound_sum<NCH>(ex);
+                        if (S.tidx[T_SUBHMR + (0)] == i) {
+                            S.tcap[T_SUBHMR + (0)][0] = r;
+                            S.tcap[T_SUBHMR + (0)][1] = bound_sum<NCH>(bb);
+                            S.tcap[T_SUBHMR + (0)][2] = bound_sum<NCH>(ex);
                         }
                         if (want_hmr)
                             for (int g = 0; g < 4; g++)
-                                if (S.sub_hmr_idx[1 + g] == i && in_group(g, tc)) {
-                                    S.sub_hmr_cap[1 + g][0] = r;
-                                    S.sub_hmr_cap[1 + g][1] = group_sum<NCH>(bb, g, true);
-                                    S.sub_hmr_cap[1 + g][2] = group_sum<NCH>(ex, g, true);
+                                if (S.tidx[T_SUBHMR + (1 + g)] == i && in_group(g, tc)) {
+                                    S.tcap[T_SUBHMR + (1 + g)][0] = r;
+                                    S.tcap[T_SUBHMR + (1 + g)][1] = group_sum<NCH>(bb, g, true);
+                                    S.tcap[T_SUBHMR + (1 + g)][2] = group_sum<NCH>(ex, g, true);
                                 }
                     }
                     for (int a = 0; a < n_ap; a++)
-                        if (S.ap_edge_idx[a] == i) {
+                        if (S.tidx[T_APEDGE + (a)] == i) {
 #pragma unroll
-                            for (int ch = 0; ch < NCH; ch++) S.ap_edge_cap[a][ch] = ex[ch];
+                            for (int ch = 0; ch < NCH; ch++) S.tcap[T_APEDGE + (a)][ch] = ex[ch];
                         }
                 }
             }
@@ -867,14 +968,24 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             argmax_reduce<NCH>(amU, S);
             argmax_reduce<NCH>(amS, S);
         }
+        if (CS > 1) {
+            if (threadIdx.x == 0) {
+                S.pub_v[0] = amU.v; S.pub_r[0] = amU.r; S.pub_i[0] = amU.i;
+                S.pub_v[1] = amS.v; S.pub_r[1] = amS.r; S.pub_i[1] = amS.i;
+            }
+            csync();  // every CTA's pass B results are visible
+            merge_targets();
+            if (crank == 0 && threadIdx.x == 0)
+                for (unsigned int rk = 1; rk < CS; rk++) {
+                    const ScanShared<NCH>* P = peer(rk);
+                    amU.offer(P->pub_v[0], P->pub_r[0], P->pub_i[0]);
+                    amS.offer(P->pub_v[1], P->pub_r[1], P->pub_i[1]);
+                }
+        }
         __syncthreads();
 
-        // --------------------------------------- thread 0: SO solve + checks
-        __shared__ int s_fail;       // 0 ok, 1 retry, >=2 fatal status
-        __shared__ double s_required;
-        __shared__ double s_so_r[SOAP_MAX_SO];
-        __shared__ int s_commit_lo, s_commit_hi;
-        if (threadIdx.x == 0) {
+        // ------------------------- rank 0, thread 0: SO solve + checks
+        if (threadIdx.x == 0 && crank == 0) {
             {
                 // innermost particle over the halo's work items (SO_properties.py:407-409)
                 unsigned long long mr = ~0ull;
@@ -897,7 +1008,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             const int p0 = ha.ndone[h];
             int p = p0;
             const double r_last = n > 0 ? __longlong_as_double((long long)R[n - 1].rbits) : 0.0;
-            for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; s_so_r[q] = 0.0; }
+            for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; S.so_r_[q] = 0.0; }
             while (p < nprops && !fail) {
                 if (p < off_so) {
                     // BoundSubhalo particle count (subhalo_properties.py:2632-2646)
@@ -911,24 +1022,24 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                 double SO_r = 0.0, SO_mass = 0.0;
                 const uint32_t nr_parts = n > nskip_so ? n - nskip_so : 0u;
                 if (nr_parts > 0) {
-                    uint32_t i = S.so_idx[q];
+                    uint32_t i = S.tidx[T_SO + (q)];
                     if (i == NONE) {
                         // no particle below the threshold (SO_properties.py:147-156)
                         if (r_last > cfg.r20) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
                         else { fail = 1; required = 0.0; }
                     } else if (i == nskip_so) {
                         // all below: SO_properties.py:157-177
-                        uint32_t ip = S.nonneg_idx;
+                        uint32_t ip = S.tidx[T_NONNEG];
                         if (ip == NONE) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
                         else {
-                            double rp = S.nonneg_cap[0], cmp = S.nonneg_cap[1];
+                            double rp = S.tcap[T_NONNEG][0], cmp = S.tcap[T_NONNEG][1];
                             SO_r = sqrt(0.75 * cmp / (SOAP_PI * rp * rho));
                             SO_mass = cmp * SO_r / rp;
                         }
                     } else {
                         // intersecting interval (SO_properties.py:180-201)
-                        double r2 = S.so_cap[q][0];
-                        double cum2 = S.so_cap[q][1], cum1 = S.so_cap[q][2];
+                        double r2 = S.tcap[T_SO + (q)][0];
+                        double cum2 = S.tcap[T_SO + (q)][1], cum1 = S.tcap[T_SO + (q)][2];
                         double r1 = __longlong_as_double((long long)R[i - 1].rbits);
                         float M1 = so_cm32(cum1, r1, cfg.nu), M2 = so_cm32(cum2, r2, cfg.nu);
                         bool ab1 = so_density(M1, r1) > rho, ab2 = so_density(M2, r2) > rho;
@@ -965,7 +1076,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     sr->so_r[q] = SO_r;
                     sr->so_mass[q] = SO_mass;
                     sr->so_exists[q] = (SO_r > 0.0 && SO_mass > 0.0) ? 1 : 0;  // SO_properties.py:457
-                    s_so_r[q] = sr->so_exists[q] ? SO_r : 0.0;
+                    S.so_r_[q] = sr->so_exists[q] ? SO_r : 0.0;
                 }
                     }
                 } else {
@@ -978,14 +1089,14 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             ha.commit_lo[h] = p0;
             ha.commit_hi[h] = p;
             ha.ndone[h] = p;
-            s_commit_lo = p0;
-            s_commit_hi = p;
+            S.commit_lo_ = p0;
+            S.commit_hi_ = p;
             if (p > p0 && fail < 2) atomicAdd(&ctr->mom_pairs, (unsigned long long)n);
             if (!fail && p >= nprops) {
                 (ha.out + (int64_t)h * ha.ncol)[3] = (double)n;
             }
-            s_fail = fail;
-            s_required = required;
+            S.fail_ = fail;
+            S.required_ = required;
             if (fail >= 2) {
                 ha.status[h] = status;
                 ha.state[h] = ST_DONE_FAIL;
@@ -995,7 +1106,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                 ha.state[h] = ST_FINAL;
                 atomicAdd(&ctr->pairs, (unsigned long long)n);
             }
-            if (fail < 2 && cfg.do_sub && s_commit_lo == 0 && s_commit_hi >= 1) {
+            if (fail < 2 && cfg.do_sub && S.commit_lo_ == 0 && S.commit_hi_ >= 1) {
                 // subhalo scan results
                 sr->sub_vmax_u_r = amU.i == NONE ? 0.0 : amU.r;
                 sr->sub_vmax_u_v = amU.i == NONE ? 0.0 : amU.v;
@@ -1021,9 +1132,9 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                 // half-mass radii of the bound subhalo (half_mass_radius.py:64-80)
                 for (int g = 0; g < 5; g++) {
                     double hm = 0.0;
-                    uint32_t i = S.sub_hmr_idx[g];
+                    uint32_t i = S.tidx[T_SUBHMR + (g)];
                     if (cfg.do_sub && Mb_g[g] != 0.0 && i != NONE) {
-                        double rmax_ = S.sub_hmr_cap[g][0], Wmax = S.sub_hmr_cap[g][1], Wmin = S.sub_hmr_cap[g][2];
+                        double rmax_ = S.tcap[T_SUBHMR + (g)][0], Wmax = S.tcap[T_SUBHMR + (g)][1], Wmin = S.tcap[T_SUBHMR + (g)][2];
                         double rmin_ = 0.0;
                         // previous member of the subset (walk back over the sorted records)
                         for (uint32_t j = i; j-- > 0;) {
@@ -1043,31 +1154,45 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             }
         }
         __syncthreads();
-        // pass C serves the SOs and apertures committed at this rung
-        const int c_so_lo = cfg.do_sub ? 1 : 0, c_ap_lo = c_so_lo + cfg.n_so;
-        const bool so_committed = n_so > 0 && s_commit_hi > s_commit_lo && s_commit_lo < c_ap_lo && s_commit_hi > c_so_lo;
-        const bool ap_committed = n_ap > 0 && s_commit_hi > c_ap_lo && s_commit_hi > s_commit_lo;
-        const bool need_c = s_fail < 2 && (so_committed || (ap_committed && want_hmr));
-        if (!need_c) continue;
-
-        // ------------------------------------------------------------ pass C
         // aperture half-mass thresholds from the edge captures (totals inside)
-        if (threadIdx.x < n_ap * 4) {
+        if (crank == 0 && threadIdx.x < n_ap * 4) {
             int a = threadIdx.x / 4, g = threadIdx.x % 4;
             double t[NCH];
-            if (S.ap_edge_idx[a] == NONE) {
+            if (S.tidx[T_APEDGE + (a)] == NONE) {
                 for (int ch = 0; ch < NCH; ch++) t[ch] = S.tot[ch];
             } else {
-                for (int ch = 0; ch < NCH; ch++) t[ch] = S.ap_edge_cap[a][ch];
+                for (int ch = 0; ch < NCH; ch++) t[ch] = S.tcap[T_APEDGE + (a)][ch];
             }
             S.ap_thr[a][g] = 0.5 * group_sum<NCH>(t, g, cfg.ap_incl[a] == 0);
         }
-        if (threadIdx.x < NCH) { S.carry[threadIdx.x] = 0.0; S.carryc[threadIdx.x] = 0; }
+        if (CS > 1) {
+            csync();  // rank 0's solve outcome is visible
+            if (crank != 0) {
+                const ScanShared<NCH>* P = peer(0);
+                if (threadIdx.x == 0) {
+                    S.fail_ = P->fail_; S.commit_lo_ = P->commit_lo_; S.commit_hi_ = P->commit_hi_;
+                }
+                if (threadIdx.x < SOAP_MAX_SO) S.so_r_[threadIdx.x] = P->so_r_[threadIdx.x];
+                if (threadIdx.x < SOAP_MAX_APERTURES * 4)
+                    S.ap_thr[threadIdx.x / 4][threadIdx.x % 4] = P->ap_thr[threadIdx.x / 4][threadIdx.x % 4];
+            }
+        }
+        __syncthreads();
+        // pass C serves the SOs and apertures committed at this rung
+        const int c_so_lo = cfg.do_sub ? 1 : 0, c_ap_lo = c_so_lo + cfg.n_so;
+        const bool so_committed = n_so > 0 && S.commit_hi_ > S.commit_lo_ && S.commit_lo_ < c_ap_lo && S.commit_hi_ > c_so_lo;
+        const bool ap_committed = n_ap > 0 && S.commit_hi_ > c_ap_lo && S.commit_hi_ > S.commit_lo_;
+        const bool need_c = S.fail_ < 2 && (so_committed || (ap_committed && want_hmr));
+        // (uniform over the cluster: everyone leaves or everyone stays)
+        if (!need_c) { csync(); continue; }
+
+        // ------------------------------------------------------------ pass C
+        if (threadIdx.x < NCH) { S.carry[threadIdx.x] = S.carry_in[threadIdx.x]; S.carryc[threadIdx.x] = S.carryc_in[threadIdx.x]; }
         __syncthreads();
         ArgMax amSO[SOAP_MAX_SO];
 #pragma unroll
         for (int q = 0; q < SOAP_MAX_SO; q++) amSO[q].init();
-        for (uint32_t tile = 0; tile < ntile; tile++) {
+        for (uint32_t tile = t_lo; tile < t_hi; tile++) {
             const uint32_t i0 = tile * SCAN_TILE + threadIdx.x * SCAN_K;
             Rec rc[SCAN_K];
             double base[NCH];
@@ -1107,12 +1232,12 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                 const double rs = fmax(cfg.soft[tc], r);
 #pragma unroll
                 for (int q = 0; q < SOAP_MAX_SO; q++)
-                    if (q < n_so && s_so_r[q] > 0.0) {
+                    if (q < n_so && S.so_r_[q] > 0.0) {
                         // Vmax_soft inside the SO (SO_properties.py:573-600)
-                        if (r < s_so_r[q] && rs > 0.0 && (min_soft > 1e-8 || pos_all >= S.n_zero))
+                        if (r < S.so_r_[q] && rs > 0.0 && (min_soft > 1e-8 || pos_all >= S.n_zero))
                             amSO[q].offer(call_in / rs, rs, i);
                         // first dark matter particle outside (SO_properties.py:471-482)
-                        if (tc == 1u && r > s_so_r[q] && i < S.dm_out_idx[q]) atomicMin(&S.dm_out_idx[q], i);
+                        if (tc == 1u && r > S.so_r_[q] && i < S.tidx[T_DMOUT + (q)]) atomicMin(&S.tidx[T_DMOUT + (q)], i);
                     }
                 if (want_hmr)
                     for (int a = 0; a < n_ap; a++) {
@@ -1122,7 +1247,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                         for (int g = 0; g < 4; g++)
                             if (in_group(g, tc) && S.ap_thr[a][g] > 0.0) {
                                 double w = group_sum<NCH>(base, g, cfg.ap_incl[a] == 0);
-                                if (w >= S.ap_thr[a][g] && i < S.ap_hmr_idx[a][g]) atomicMin(&S.ap_hmr_idx[a][g], i);
+                                if (w >= S.ap_thr[a][g] && i < S.tidx[T_APHMR + (a) * 4 + (g)]) atomicMin(&S.tidx[T_APHMR + (a) * 4 + (g)], i);
                             }
                     }
             }
@@ -1146,14 +1271,14 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     for (int ch = 0; ch < NCH; ch++)
                         if (c == ch) bb[ch] += m;
                     for (int q = 0; q < n_so; q++)
-                        if (S.dm_out_idx[q] == i) { S.dm_out_cap[q][0] = r; S.dm_out_cap[q][1] = m; }
+                        if (S.tidx[T_DMOUT + (q)] == i) { S.tcap[T_DMOUT + (q)][0] = r; S.tcap[T_DMOUT + (q)][1] = m; }
                     if (want_hmr)
                         for (int a = 0; a < n_ap; a++)
                             for (int g = 0; g < 4; g++)
-                                if (S.ap_hmr_idx[a][g] == i && in_group(g, tc)) {
-                                    S.ap_hmr_cap[a][g][0] = r;
-                                    S.ap_hmr_cap[a][g][1] = group_sum<NCH>(bb, g, cfg.ap_incl[a] == 0);
-                                    S.ap_hmr_cap[a][g][2] = group_sum<NCH>(ex, g, cfg.ap_incl[a] == 0);
+                                if (S.tidx[T_APHMR + (a) * 4 + (g)] == i && in_group(g, tc)) {
+                                    S.tcap[T_APHMR + (a) * 4 + (g)][0] = r;
+                                    S.tcap[T_APHMR + (a) * 4 + (g)][1] = group_sum<NCH>(bb, g, cfg.ap_incl[a] == 0);
+                                    S.tcap[T_APHMR + (a) * 4 + (g)][2] = group_sum<NCH>(ex, g, cfg.ap_incl[a] == 0);
                                 }
                 }
             }
@@ -1163,25 +1288,38 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
         for (int q = 0; q < SOAP_MAX_SO; q++)
             if (q < n_so) {
                 argmax_reduce<NCH>(amSO[q], S);
-                if (threadIdx.x == 0) {
+                if (CS > 1 && threadIdx.x == 0) {
+                    S.pub_v[2 + q] = amSO[q].v; S.pub_r[2 + q] = amSO[q].r; S.pub_i[2 + q] = amSO[q].i;
+                }
+            }
+        if (CS > 1) {
+            csync();  // every CTA's pass C results are visible
+            merge_targets();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && crank == 0) {
+#pragma unroll
+            for (int q = 0; q < SOAP_MAX_SO; q++)
+                if (q < n_so) {
+                    for (unsigned int rk = 1; rk < CS; rk++) {
+                        const ScanShared<NCH>* P = peer(rk);
+                        amSO[q].offer(P->pub_v[2 + q], P->pub_r[2 + q], P->pub_i[2 + q]);
+                    }
                     sr->so_vmax_r[q] = amSO[q].i == NONE ? 0.0 : amSO[q].r;
                     sr->so_vmax_v[q] = amSO[q].i == NONE ? 0.0 : amSO[q].v;
                 }
-            }
-        __syncthreads();
-        if (threadIdx.x == 0) {
             for (int q = 0; q < n_so; q++) {
                 // dm_missed_mass (SO_properties.py:471-482)
                 double missed = 0.0;
-                uint32_t i = S.dm_out_idx[q];
-                if (s_so_r[q] > 0.0 && i != NONE) {
-                    double r2 = S.dm_out_cap[q][0], m2 = S.dm_out_cap[q][1];
+                uint32_t i = S.tidx[T_DMOUT + (q)];
+                if (S.so_r_[q] > 0.0 && i != NONE) {
+                    double r2 = S.tcap[T_DMOUT + (q)][0], m2 = S.tcap[T_DMOUT + (q)][1];
                     for (uint32_t j = i; j-- > 0;) {
                         uint32_t f = R[j].flags;
                         uint32_t tcj = NCH == 2 ? 1u : (f & 3u);
                         if (tcj == 1u) {
                             double r1 = __longlong_as_double((long long)R[j].rbits);
-                            missed = m2 * (s_so_r[q] - r1) / (r2 - r1);
+                            missed = m2 * (S.so_r_[q] - r1) / (r2 - r1);
                             break;
                         }
                     }
@@ -1191,9 +1329,9 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
             for (int a = 0; a < n_ap; a++)
                 for (int g = 0; g < 4; g++) {
                     double hm = 0.0;
-                    uint32_t i = S.ap_hmr_idx[a][g];
+                    uint32_t i = S.tidx[T_APHMR + (a) * 4 + (g)];
                     if (want_hmr && S.ap_thr[a][g] > 0.0 && i != NONE) {
-                        double rmax_ = S.ap_hmr_cap[a][g][0], Wmax = S.ap_hmr_cap[a][g][1], Wmin = S.ap_hmr_cap[a][g][2];
+                        double rmax_ = S.tcap[T_APHMR + (a) * 4 + (g)][0], Wmax = S.tcap[T_APHMR + (a) * 4 + (g)][1], Wmin = S.tcap[T_APHMR + (a) * 4 + (g)][2];
                         double rmin_ = 0.0;
                         for (uint32_t j = i; j-- > 0;) {
                             uint32_t f = R[j].flags;
@@ -1210,7 +1348,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_solve(HaloArrays ha, DevCfg cf
                     sr->ap_hmr[a][g] = hm;
                 }
         }
-        __syncthreads();
+        csync();  // rank 0 is done reading the other CTAs' shared memory
     }
 }
 
@@ -1344,11 +1482,12 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(listA, uint32_t, h, "h_listA", H);
     WS_GET(listB, uint32_t, h, "h_listB", H);
     WS_GET(try_list, uint32_t, h, "h_try", H);
+    WS_GET(big_list, uint32_t, h, "h_big", H);
     WS_GET(multi_list, uint32_t, h, "h_multi", H);
     WS_GET(ctr, Counters, h, "h_ctr", 2);
     WS_GET(n_pend_dev, unsigned int, h, "h_npend", 4);
     // work items: every halo has at least one; large spheres are cut every ITEM_CAND candidates
-    const size_t items_cap = (size_t)H + (size_t)(16 * (v.n / ITEM_CAND + 1)) + 1024;
+    size_t items_cap = (size_t)H + (size_t)(16 * (v.n / ITEM_CAND + 1)) + 1024;
     WS_GET(items, Item, h, "h_items", items_cap);
     WS_GET(item_minr, unsigned long long, h, "h_item_minr", items_cap);
     WS_GET(item_minfof, int32_t, h, "h_item_minfof", items_cap);
@@ -1380,11 +1519,28 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         LAUNCH(h, k_plan_items, grid_for(n_pend, 128), 128, 0, stream, v, ha, pend, n_pend_dev, items,
                (unsigned int)items_cap, ctr);
         log.end(stream);
+        {
+            // coarse meshes / huge spheres can need more work items than provisioned
+            Counters pc;
+            CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (pc.items_overflow) {
+                if (pc.n_items >= 0xfff00000u) SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", pc.n_items);
+                items_cap = (size_t)pc.n_items + 1024;
+                items = (Item*)h->get("h_items", sizeof(Item) * items_cap);
+                item_minr = (unsigned long long*)h->get("h_item_minr", sizeof(unsigned long long) * items_cap);
+                item_minfof = (int32_t*)h->get("h_item_minfof", sizeof(int32_t) * items_cap);
+                if (!items || !item_minr || !item_minfof) return -1;
+                CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
+                LAUNCH(h, k_plan_items, grid_for(n_pend, 128), 128, 0, stream, v, ha, pend, n_pend_dev, items,
+                       (unsigned int)items_cap, ctr);
+            }
+        }
         log.begin("count", stream);
         LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr);
         log.end(stream);
         log.begin("gate", stream);
-        LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list,
+        LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
                multi_list, next, ctr);
         log.end(stream);
         Counters hc;
@@ -1394,8 +1550,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
-        if (hc.n_try > 0) {
-            const unsigned int n_try = hc.n_try;
+        if (hc.n_try + hc.n_big > 0) {
+            const unsigned int n_try = hc.n_try + hc.n_big;
             // workspace for this round
             Rec* recs = (Rec*)h->get("h_recs", sizeof(Rec) * (size_t)(hc.rec_total + 1));
             if (!recs) return -1;
@@ -1408,19 +1564,19 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             int64_t* fine_excl = (int64_t*)h->get("h_fine_excl", sizeof(int64_t) * (size_t)(hc.n_fine + 1));
             if (!bkt_small || !bkt_big || !bkt_huge || !fine_cnt || !fine_cur || !fine_excl) return -1;
             unsigned int* n_try_dev = &ctr->n_try;
-            unsigned int* n_multi_dev = &ctr->n_multi;
             if (hc.n_multi > 0) {
                 log.begin("fine_hist", stream);
                 CUDA_TRY(cudaMemsetAsync(fine_cnt, 0, sizeof(uint32_t) * (hc.n_fine + 1), stream));
                 CUDA_TRY(cudaMemsetAsync(fine_cur, 0, sizeof(uint32_t) * (hc.n_fine + 1), stream));
                 LAUNCH(h, k_fine_hist_halo, sweep_grid, TB, 0, stream, v, ha, items, ctr, fine_cnt);
                 if (soap_exclusive_scan_u32(h, fine_cnt, nullptr, fine_excl, hc.n_fine + 1, nullptr, stream)) return -1;
-                LAUNCH(h, k_build_buckets, grid_for(hc.n_multi, 64), 64, 0, stream, ha, multi_list, n_multi_dev,
-                       fine_excl, fine_cnt, 0ull, ctr, bkt_small, bkt_big, bkt_huge);
+                LAUNCH(h, k_build_buckets, hc.n_multi, 256, 0, stream, ha, multi_list, fine_excl, ctr, bkt_small,
+                       bkt_big, bkt_huge);
                 log.end(stream);
             }
-            LAUNCH(h, k_single_buckets, grid_for(n_try, 128), 128, 0, stream, ha, try_list, n_try_dev, ctr,
-                   bkt_small, bkt_big);
+            if (hc.n_try > 0)
+                LAUNCH(h, k_single_buckets, grid_for(hc.n_try, 128), 128, 0, stream, ha, try_list, n_try_dev, ctr,
+                       bkt_small, bkt_big);
             log.begin("collect", stream);
             LAUNCH(h, k_collect, sweep_grid, TB, 0, stream, v, ha, dc, items, fine_excl, fine_cur, ctr, recs,
                    item_minr, item_minfof);
@@ -1439,14 +1595,24 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             }
             log.end(stream);
             log.begin("scan_solve", stream);
-            {
-                unsigned int g = n_try < (unsigned)(sm * 8) ? n_try : (unsigned)(sm * 8);
+            if (hc.n_try > 0) {
+                unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
                 if (cfg->dmo)
-                    LAUNCH(h, k_scan_solve<2>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr,
-                           item_minr, item_minfof);
+                    LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next,
+                           ctr, item_minr, item_minfof);
                 else
-                    LAUNCH(h, k_scan_solve<8>, g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next, ctr,
-                           item_minr, item_minfof);
+                    LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next,
+                           ctr, item_minr, item_minfof);
+            }
+            if (hc.n_big > 0) {
+                // one cluster of SCAN_CS CTAs per large halo
+                unsigned int ncl = hc.n_big < (unsigned)(sm * 2 / SCAN_CS) ? hc.n_big : (unsigned)(sm * 2 / SCAN_CS);
+                if (cfg->dmo)
+                    LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, stream, ha, dc, big_list,
+                           &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+                else
+                    LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, stream, ha, dc, big_list,
+                           &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
             }
             log.end(stream);
             log.begin("moments", stream);

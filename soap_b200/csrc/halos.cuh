@@ -132,13 +132,15 @@ struct HaloArrays {
 };
 
 // A work item = a contiguous range [first, first+count) of a halo's candidate
-// stream (its rows concatenated in row order).
+// stream (its rows concatenated in row order).  row0 / pos0 locate the first
+// row that overlaps the range (pos0 = stream offset at the start of row0), so a
+// sweep never walks the rows in front of its range.
 struct Item {
-    uint32_t halo, first, count, pad;
+    uint32_t halo, first, count, row0;
+    uint32_t pos0, k, pad0, pad1;
 };
-constexpr uint32_t ITEM_CAND = 32768;  // candidates per item
-constexpr int SWEEP_MAXP = 64;         // row pieces per batch
-constexpr uint32_t LONG_PIECE = 1024;  // longer pieces are swept by the whole CTA
+constexpr uint32_t ITEM_CAND = 16384;  // candidates per item
+constexpr int SWEEP_NT = 256;          // threads of every sweeping kernel = rows per batch
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int range_total(const DimRanges& r) {
@@ -185,94 +187,82 @@ __device__ __forceinline__ void halo_ranges(const ChunkView& v, double cx, doubl
     dim_ranges(c, r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
 }
 
-struct Piece {
-    uint32_t s0, s1;
-};
+// Load-balanced sweep state: one batch = up to SWEEP_NT rows; every row piece
+// inside the item's range is cut into 32-candidate chunks and the chunks are
+// dealt round-robin to the warps (no warp waits for a long row).
 struct SweepShared {
     DimRanges rg[3];
-    Piece pieces[SWEEP_MAXP];
-    int np, row, done;
-    uint32_t pos;
+    uint32_t s0[SWEEP_NT];        // first particle of the row piece
+    uint32_t len[SWEEP_NT];       // candidates of the row piece
+    uint32_t cpre[SWEEP_NT + 1];  // exclusive prefix of chunk counts
+    unsigned long long wlen[SWEEP_NT / 32];
+    uint32_t wchk[SWEEP_NT / 32];
+    unsigned long long pos_next;
 };
 
-// warp 0: collect the next batch of row pieces of the stream range [a, b)
-__device__ inline void sweep_build_batch(const ChunkView& v, SweepShared& S, const RowIter& ri,
-                                         uint32_t a, uint32_t b) {
-    const int lane = threadIdx.x & 31;
-    int np = 0, row = S.row;
-    uint32_t pos = S.pos;
-    while (row < ri.nrows && pos < b && np < SWEEP_MAXP) {
-        const int r = row + lane;
-        uint32_t s0 = 0, s1 = 0;
-        if (r < ri.nrows) row_span(v, S.rg, ri, r, s0, s1);
-        const uint32_t len = s1 - s0;
-        uint32_t incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t end = pos + incl, start = end - len;
-        const uint32_t lo = a > start ? a : start, hi = b < end ? b : end;
-        const bool has = (r < ri.nrows) && hi > lo;
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        const int my = np + __popc(bal & ((1u << lane) - 1u));
-        const int tot = __popc(bal);
-        if (has && my < SWEEP_MAXP) {
-            Piece pc;
-            pc.s0 = s0 + (lo - start);
-            pc.s1 = s0 + (hi - start);
-            S.pieces[my] = pc;
-        }
-        if (np + tot <= SWEEP_MAXP) {
-            np += tot;
-            pos = __shfl_sync(0xffffffffu, end, 31);
-            row += 32;
-        } else {
-            const unsigned lastm = __ballot_sync(0xffffffffu, has && my == SWEEP_MAXP - 1);
-            const int Ln = __ffs(lastm) - 1;
-            np = SWEEP_MAXP;
-            pos = __shfl_sync(0xffffffffu, end, Ln);
-            row += Ln + 1;
-        }
-    }
-    if (lane == 0) {
-        S.np = np;
-        S.row = row;
-        S.pos = pos;
-        S.done = !(row < ri.nrows && pos < b);
-    }
-}
-
-// Sweep the candidates [a, b) of a halo's stream with the whole CTA.  f(t, ok)
-// is called warp-synchronously: every lane of a warp calls it together, ok
-// tells whether t is a real candidate.
-template <int NT, class F>
+// Sweep the candidates of work item im with the whole CTA (SWEEP_NT threads).
+// f(t, ok) is called warp-synchronously: all 32 lanes of a warp call it
+// together, ok tells whether particle slot t is a real candidate of the lane.
+template <class F>
 __device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx, double cy, double cz,
-                                  double r, uint32_t a, uint32_t b, F f) {
+                                  double r, const Item& im, F f) {
+    constexpr int NT = SWEEP_NT, NW = SWEEP_NT / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long a = im.first, b = (unsigned long long)im.first + im.count;
     __syncthreads();
     if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, r, S.rg);
-    if (threadIdx.x == 0) { S.row = 0; S.pos = 0; S.done = 0; S.np = 0; }
     __syncthreads();
     const RowIter ri = row_iter(S.rg);
+    int row_base = (int)im.row0;
+    unsigned long long pos_base = im.pos0;
     while (true) {
-        if (wid == 0) sweep_build_batch(v, S, ri, a, b);
-        __syncthreads();
-        const bool done = S.done != 0;
-        const int np = S.np;
-        for (int p = wid; p < np; p += NT / 32) {
-            const Piece pc = S.pieces[p];
-            if (pc.s1 - pc.s0 > LONG_PIECE) continue;
-            for (uint32_t t0 = pc.s0; t0 < pc.s1; t0 += 32) f(t0 + lane, t0 + lane < pc.s1);
+        const int row = row_base + (int)threadIdx.x;
+        uint32_t s0 = 0, s1 = 0;
+        if (row < ri.nrows) row_span(v, S.rg, ri, row, s0, s1);
+        const uint32_t len = s1 - s0;
+        unsigned long long incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        for (int p = 0; p < np; p++) {
-            const Piece pc = S.pieces[p];
-            if (pc.s1 - pc.s0 <= LONG_PIECE) continue;
-            for (uint32_t t0 = pc.s0 + wid * 32; t0 < pc.s1; t0 += NT) f(t0 + lane, t0 + lane < pc.s1);
-        }
+        if (lane == 31) S.wlen[wid] = incl;
         __syncthreads();
-        if (done) break;
+        unsigned long long base = pos_base;
+        for (int w = 0; w < wid; w++) base += S.wlen[w];
+        const unsigned long long end = base + incl, start = end - len;
+        const unsigned long long lo = a > start ? a : start, hi = b < end ? b : end;
+        const uint32_t clen = hi > lo ? (uint32_t)(hi - lo) : 0u;
+        uint32_t cincl = (clen + 31u) >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, cincl, o);
+            if (lane >= o) cincl += t;
+        }
+        if (lane == 31) S.wchk[wid] = cincl;
+        S.s0[threadIdx.x] = s0 + (uint32_t)(lo - start);
+        S.len[threadIdx.x] = clen;
+        if (threadIdx.x == NT - 1) S.pos_next = end;
+        __syncthreads();
+        uint32_t cbase = 0;
+        for (int w = 0; w < wid; w++) cbase += S.wchk[w];
+        S.cpre[threadIdx.x + 1] = cbase + cincl;
+        if (threadIdx.x == 0) S.cpre[0] = 0;
+        __syncthreads();
+        const uint32_t total = S.cpre[NT];
+        for (uint32_t c = wid; c < total; c += NW) {
+            int jl = 0, jh = NT;  // largest jl with cpre[jl] <= c
+            while (jh - jl > 1) {
+                const int mid = (jl + jh) >> 1;
+                if (S.cpre[mid] <= c) jl = mid; else jh = mid;
+            }
+            const uint32_t off = (c - S.cpre[jl]) * 32u + (uint32_t)lane;
+            f(S.s0[jl] + off, off < S.len[jl]);
+        }
+        pos_base = S.pos_next;
+        row_base += NT;
+        __syncthreads();
+        if (row_base >= ri.nrows || pos_base >= b) break;
     }
 }
 #endif

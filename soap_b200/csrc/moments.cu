@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int TB = 256;
+constexpr int TB = SWEEP_NT;
 constexpr int MAX_CUTS = SOAP_MAX_SO + SOAP_MAX_APERTURES + 2;
 
 enum { V_N = 0, V_M, V_MX, V_MV = 5, V_ML = 8, V_MR = 11, V_MRS, V_SAT, V_EXT, V_MIN = 15,
@@ -52,25 +52,6 @@ __device__ inline int find_cut(const Cuts& c, double r, int strict) {
         if (c.r[k] == r && c.strict[k] == strict) return k;
     return -1;
 }
-
-template <int V>
-struct Acc {
-    double v[V];
-    int key;
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < V; i++) v[i] = 0.0;
-    }
-    __device__ __forceinline__ void flush(double* banks) {
-        if (key >= 0) {
-            double* b = banks + (size_t)key * V;
-#pragma unroll
-            for (int i = 0; i < V; i++)
-                if (v[i] != 0.0) atomicAdd(&b[i], v[i]);
-        }
-        clear();
-    }
-};
 
 // sum banks over shells [0, pos], bound states and types selected by masks
 template <int V>
@@ -191,9 +172,17 @@ template <int V, int NTY>
 __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevCfg cfg,
                                                 const Item* __restrict__ items,
                                                 const unsigned int* __restrict__ n_items_dev,
-                                                double* __restrict__ gbanks, int gbank_stride) {
+                                                double* __restrict__ gbanks, int gbank_stride, int priv) {
+    // dynamic shared memory: [priv ? NW : 1][gbank_stride] banks, then the
+    // per-warp staging tiles [NW][32][VP] and their keys [NW][32]
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = TB / 32;
+    constexpr int VP = V | 1;  // odd row stride: conflict-free 64-bit stores
     double* banks = (double*)smem_raw;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* stage_w = banks + (size_t)(priv ? NW : 1) * gbank_stride + (size_t)wid * 32 * VP;
+    int* skey_w = (int*)(banks + (size_t)(priv ? NW : 1) * gbank_stride + (size_t)NW * 32 * VP) + wid * 32;
+    double* bank_w = banks + (priv ? (size_t)wid * gbank_stride : 0);
     __shared__ SweepShared SW;
     __shared__ Cuts cuts;
     __shared__ int s_last;
@@ -233,62 +222,122 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
         __syncthreads();
         const int ncut = cuts.n;
         const int nbank = (ncut + 1) * 2 * NTY;
-        for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = 0.0;
+        if (priv) {
+            for (int w = 0; w < NW; w++)
+                for (int i = threadIdx.x; i < nbank * V; i += TB) banks[(size_t)w * gbank_stride + i] = 0.0;
+        } else {
+            for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = 0.0;
+        }
         __syncthreads();
         const int32_t cen_fof = sr->cen_fof;
-        Acc<V> acc;
-        acc.key = -1;
-        acc.clear();
-        sweep_item<TB>(v, SW, cx, cy, cz, R, im.first, im.first + im.count, [&](uint32_t t, bool ok) {
-            if (!ok) return;
-            double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
-            if (!(r2 <= r2max)) return;
-            const double x = rewrap_rel(v.px[t], cx, L, halfL);
-            const double y = rewrap_rel(v.py[t], cy, L, halfL);
-            const double z = rewrap_rel(v.pz[t], cz, L, halfL);
-            const double r = radius3(x, y, z);
-            int shell = 0;
-            for (int k = 0; k < ncut; k++) shell += cuts.strict[k] ? !(r < cuts.r[k]) : !(r <= cuts.r[k]);
-            const int32_t g = v.grnr[t];
-            const int bound = g == hidx;
-            const uint32_t tc = NTY == 1 ? 1u : (uint32_t)v.type[t];
-            const int key = (shell * 2 + bound) * NTY + (NTY == 1 ? 0 : (int)tc);
-            if (key != acc.key) { acc.flush(banks); acc.key = key; }
-            const double m = (double)v.mass[t];
-            const double vx = (double)v.vx[t], vy = (double)v.vy[t], vz = (double)v.vz[t];
-            acc.v[V_N] += 1.0;
-            acc.v[V_M] += m;
-            acc.v[V_MX] += m * x; acc.v[V_MX + 1] += m * y; acc.v[V_MX + 2] += m * z;
-            acc.v[V_MV] += m * vx; acc.v[V_MV + 1] += m * vy; acc.v[V_MV + 2] += m * vz;
-            acc.v[V_ML] += m * (y * vz - z * vy);
-            acc.v[V_ML + 1] += m * (z * vx - x * vz);
-            acc.v[V_ML + 2] += m * (x * vy - y * vx);
-            acc.v[V_MR] += m * r;
-            acc.v[V_MRS] += m * fmax(cfg.soft[tc], r);
-            if (!bound && g >= 0) {
-                // SO_properties.py:461-466
-                if (v.fof[t] == cen_fof) acc.v[V_SAT] += m; else acc.v[V_EXT] += m;
-            }
-            if constexpr (V >= V_FULL) {
-                acc.v[V_VV] += m * vx * vx; acc.v[V_VV + 1] += m * vy * vy; acc.v[V_VV + 2] += m * vz * vz;
-                acc.v[V_VV + 3] += m * vx * vy; acc.v[V_VV + 4] += m * vx * vz; acc.v[V_VV + 5] += m * vy * vz;
-                acc.v[V_XV] += m * (x * vx + y * vy + z * vz);
-                const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
-                acc.v[V_XX] += m * xx; acc.v[V_XX + 1] += m * yy; acc.v[V_XX + 2] += m * zz;
-                acc.v[V_XX + 3] += m * xy; acc.v[V_XX + 4] += m * xz; acc.v[V_XX + 5] += m * yz;
-                const double nrm = r * r;
-                if (nrm <= 1e-8) {  // np.isclose(norm, 0): inertia_tensors.py:62-64
-                    acc.v[V_M0] += m; acc.v[V_N0] += 1.0;
-                } else {
-                    const double w = m / nrm;
-                    acc.v[V_XXR] += w * xx; acc.v[V_XXR + 1] += w * yy; acc.v[V_XXR + 2] += w * zz;
-                    acc.v[V_XXR + 3] += w * xy; acc.v[V_XXR + 4] += w * xz; acc.v[V_XXR + 5] += w * yz;
+        // Transposed accumulation: a lane computes the V moment terms of its
+        // own candidate and stages them; then lane l owns value l and the warp
+        // walks the staged particles one by one, so values of one bank are
+        // summed in registers and a bank is touched only when the key changes.
+        constexpr int NA = (V + 31) / 32;
+        double acc[NA];
+        int cur = -1;
+#pragma unroll
+        for (int q = 0; q < NA; q++) acc[q] = 0.0;
+        auto flush = [&]() {
+            if (cur >= 0) {
+                double* b = bank_w + (size_t)cur * V;
+#pragma unroll
+                for (int q = 0; q < NA; q++) {
+                    const int vi = q * 32 + lane;
+                    if (vi < V && acc[q] != 0.0) {
+                        if (priv) b[vi] += acc[q]; else atomicAdd(&b[vi], acc[q]);
+                    }
+                    acc[q] = 0.0;
                 }
             }
+        };
+        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+            bool in = false;
+            int key = 0;
+            double val[V];
+            if (ok) {
+                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+                in = r2 <= r2max;
+            }
+            if (in) {
+                const double x = rewrap_rel(v.px[t], cx, L, halfL);
+                const double y = rewrap_rel(v.py[t], cy, L, halfL);
+                const double z = rewrap_rel(v.pz[t], cz, L, halfL);
+                const double r = radius3(x, y, z);
+                int shell = 0;
+                for (int k = 0; k < ncut; k++) shell += cuts.strict[k] ? !(r < cuts.r[k]) : !(r <= cuts.r[k]);
+                const int32_t g = v.grnr[t];
+                const int bound = g == hidx;
+                const uint32_t tc = NTY == 1 ? 1u : (uint32_t)v.type[t];
+                key = (shell * 2 + bound) * NTY + (NTY == 1 ? 0 : (int)tc);
+                const double m = (double)v.mass[t];
+                const double vx = (double)v.vx[t], vy = (double)v.vy[t], vz = (double)v.vz[t];
+#pragma unroll
+                for (int i = 0; i < V; i++) val[i] = 0.0;
+                val[V_N] = 1.0;
+                val[V_M] = m;
+                val[V_MX] = m * x; val[V_MX + 1] = m * y; val[V_MX + 2] = m * z;
+                val[V_MV] = m * vx; val[V_MV + 1] = m * vy; val[V_MV + 2] = m * vz;
+                val[V_ML] = m * (y * vz - z * vy);
+                val[V_ML + 1] = m * (z * vx - x * vz);
+                val[V_ML + 2] = m * (x * vy - y * vx);
+                val[V_MR] = m * r;
+                val[V_MRS] = m * fmax(cfg.soft[tc], r);
+                if (!bound && g >= 0) {
+                    // SO_properties.py:461-466
+                    if (v.fof[t] == cen_fof) val[V_SAT] = m; else val[V_EXT] = m;
+                }
+                if constexpr (V >= V_FULL) {
+                    val[V_VV] = m * vx * vx; val[V_VV + 1] = m * vy * vy; val[V_VV + 2] = m * vz * vz;
+                    val[V_VV + 3] = m * vx * vy; val[V_VV + 4] = m * vx * vz; val[V_VV + 5] = m * vy * vz;
+                    val[V_XV] = m * (x * vx + y * vy + z * vz);
+                    const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+                    val[V_XX] = m * xx; val[V_XX + 1] = m * yy; val[V_XX + 2] = m * zz;
+                    val[V_XX + 3] = m * xy; val[V_XX + 4] = m * xz; val[V_XX + 5] = m * yz;
+                    const double nrm = r * r;
+                    if (nrm <= 1e-8) {  // np.isclose(norm, 0): inertia_tensors.py:62-64
+                        val[V_M0] = m; val[V_N0] = 1.0;
+                    } else {
+                        const double w = m / nrm;
+                        val[V_XXR] = w * xx; val[V_XXR + 1] = w * yy; val[V_XXR + 2] = w * zz;
+                        val[V_XXR + 3] = w * xy; val[V_XXR + 4] = w * xz; val[V_XXR + 5] = w * yz;
+                    }
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (bal == 0u) return;
+            if (in) {
+                const int slot = __popc(bal & ((1u << lane) - 1u));
+                double* st = stage_w + slot * VP;
+#pragma unroll
+                for (int i = 0; i < V; i++) st[i] = val[i];
+                skey_w[slot] = key;
+            }
+            __syncwarp();
+            const int cnt = __popc(bal);
+            for (int p = 0; p < cnt; p++) {
+                const int k = skey_w[p];
+                if (k != cur) { flush(); cur = k; }
+#pragma unroll
+                for (int q = 0; q < NA; q++) {
+                    const int vi = q * 32 + lane;
+                    if (vi < V) acc[q] += stage_w[p * VP + vi];
+                }
+            }
+            __syncwarp();
         });
-        acc.flush(banks);
-        acc.key = -1;
+        flush();
+        cur = -1;
         __syncthreads();
+        if (priv) {
+            for (int i = threadIdx.x; i < nbank * V; i += TB) {
+                double s = banks[i];
+                for (int w = 1; w < NW; w++) s += banks[(size_t)w * gbank_stride + i];
+                banks[i] = s;
+            }
+            __syncthreads();
+        }
         // halos swept by several work items: combine in global banks; the last
         // item to arrive writes the result row
         const uint32_t n_it = ha.n_items[h];
@@ -441,7 +490,12 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     const int nty = cfg.dmo ? 1 : 4;
     const int V = full ? V_FULL : V_MIN;
     const int stride = (cfg.n_so + cfg.n_ap + 3) * 2 * nty * V;
-    const size_t smem = (size_t)stride * sizeof(double);
+    const int NW = TB / 32, VP = V | 1;
+    const size_t stage_bytes = (size_t)NW * 32 * VP * sizeof(double) + (size_t)NW * 32 * sizeof(int);
+    // warp-private banks when they fit next to the staging tiles
+    const int priv = ((size_t)NW * stride * sizeof(double) + stage_bytes <= 96 * 1024) ? 1 : 0;
+    const size_t smem = (size_t)(priv ? NW : 1) * stride * sizeof(double) + stage_bytes;
+    if (smem > 220 * 1024) SOAP_FAIL("soap_process_halos: %d SO + %d aperture variations need %zu bytes of shared memory", cfg.n_so, cfg.n_ap, smem);
     double* gbanks = (double*)h->get("h_gbanks", sizeof(double) * (size_t)stride * (n_mslot + 1));
     if (!gbanks) return -1;
     if (n_mslot > 0) CUDA_TRY(cudaMemsetAsync(gbanks, 0, sizeof(double) * (size_t)stride * n_mslot, stream));
@@ -452,7 +506,7 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
         CUDA_TRY(cudaFuncSetAttribute(k_moments<VV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)smem));                                                    \
         LAUNCH(h, (k_moments<VV, NT>), g, TB, smem, stream, c->v, ha, cfg, items, n_items_dev, gbanks, \
-               stride);                                                                               \
+               stride, priv);                                                                         \
     } while (0)
     if (full && nty == 4) MOM(V_FULL, 4);
     else if (full) MOM(V_FULL, 1);

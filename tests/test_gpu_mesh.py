@@ -107,3 +107,27 @@ def test_query_single_particle_and_batch():
         assert counts[q] == len(b)
         assert np.array_equal(np.sort(idx[offsets[q]:offsets[q + 1]]), b)
         assert abs(enc[q] - mass[b].astype(np.float64).sum()) <= 1e-12 * max(1.0, enc[q])
+
+
+def test_mesh_and_queries_match_reference_golden():
+    """CUDA stage A/B against fixtures produced by executing the reference's own
+    SharedMesh source (tests/golden/make_golden.py): cell arrays bit-exact, query
+    results equal as index sets (the within-cell order is unpinned upstream)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shared_mesh.npz"))
+    from soap_b200.shared_mesh import SharedMesh
+
+    L = float(g["mesh_L"])
+    for i in range(int(g["mesh_n"])):
+        pos, res = g[f"mesh{i}_pos"], int(g[f"mesh{i}_res"])
+        m = SharedMesh(None, pos, res)
+        assert np.array_equal(m.pos_min, g[f"mesh{i}_pos_min"])
+        assert np.array_equal(m.pos_max, g[f"mesh{i}_pos_max"])
+        assert np.array_equal(m.cell_size, g[f"mesh{i}_cell_size"])
+        assert np.array_equal(m.cell_count.cpu().numpy(), g[f"mesh{i}_cell_count"])
+        assert np.array_equal(m.cell_offset.cpu().numpy(), g[f"mesh{i}_cell_offset"])
+        assert np.array_equal(m.sort_idx.cpu().numpy(), g[f"mesh{i}_sort_idx"])  # stable == the generator's stand-in sort
+        for q in range(len(g[f"mesh{i}_radii"])):
+            got = m.query_radius_periodic(g[f"mesh{i}_centres"][q], g[f"mesh{i}_radii"][q], None, L)
+            assert np.array_equal(np.sort(got), g[f"mesh{i}_q{q}"]), f"mesh {i} query {q}"

@@ -1,0 +1,111 @@
+"""The oracle restatement reproduces the golden fixtures of tests/golden/, which
+were produced by executing the reference's own function bodies
+(tests/golden/make_golden.py, run in the build container).  CPU only."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import calc as oc
+from oracle import mesh as om
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    path = os.path.join(GOLD, name + ".npz")
+    assert os.path.exists(path), f"{path} missing: run tests/golden/make_golden.py in the build container"
+    return np.load(path)
+
+
+def test_find_SO_radius_and_mass_matches_reference():
+    g = _load("so_radius")
+    kinds = set()
+    for i in range(int(g["so_n"])):
+        r, dens, cm, rho = g[f"so{i}_r"], g[f"so{i}_dens"], g[f"so{i}_cm"], float(g[f"so{i}_rho"])
+        err = 0
+        try:
+            res = np.array(oc.find_SO_radius_and_mass(r, dens, cm, rho), dtype=np.float64)
+        except oc.SearchRadiusTooSmallError:
+            res, err = np.zeros(3), 1
+        except RuntimeError:
+            res, err = np.zeros(3), 2
+        assert err == int(g[f"so{i}_err"]), f"case {i}"
+        # identical numpy / scipy.brentq calls: bit-exact
+        assert np.array_equal(res, g[f"so{i}_res"]), f"case {i}: {res} vs {g[f'so{i}_res']}"
+        kinds.add((err, bool(dens[0] > rho)))
+    # the fixture exercises the interpolation branch, the all-below branch and the retry branch
+    assert {(0, True), (0, False), (1, True)} <= kinds
+
+
+def test_half_weight_radius_matches_reference():
+    g = _load("half_mass_radius")
+    for i in range(int(g["hmr_n"])):
+        r, w, tot = g[f"hmr{i}_r"], g[f"hmr{i}_w"], g[f"hmr{i}_tot"][()]
+        got = float(oc.get_half_weight_radius(r, w, tot))
+        assert got == float(g[f"hmr{i}_res"]), f"case {i}"
+        # tests/test_half_mass_radius.py:31: the half-mass radius is inside the particle set
+        if len(r) and tot > 0:
+            assert got <= r.max()
+
+
+def test_kinematics_match_reference():
+    g = _load("kinematics")
+    for i in range(int(g["kin_n"])):
+        m, pos, vel = g[f"kin{i}_m"], g[f"kin{i}_pos"], g[f"kin{i}_vel"]
+        mf = m / m.sum()
+        vcom = (mf[:, None] * vel).sum(axis=0)
+        vd = oc.get_velocity_dispersion_matrix(mf, vel, vcom)
+        assert vd.dtype == np.float32 and np.array_equal(vd, g[f"kin{i}_veldisp"])
+        L = oc.get_angular_momentum(m, pos, vel, ref_velocity=vcom)
+        assert np.array_equal(np.asarray(L, dtype=np.float64), g[f"kin{i}_L"])
+        L2, kappa, mcr = oc.get_angular_momentum_and_kappa_corot_mass_weighted(
+            m, pos, vel, reference_velocity=vcom, do_counterrot_mass=True
+        )
+        assert np.array_equal(np.asarray(L2, dtype=np.float64), g[f"kin{i}_L2"])
+        assert float(kappa) == float(g[f"kin{i}_kappa"]) and float(mcr) == float(g[f"kin{i}_Mcr"])
+        rv, vmax = oc.get_vmax(m, g[f"kin{i}_r"], 1.0)
+        assert np.array_equal(np.array([float(rv), float(vmax)]), g[f"kin{i}_vmax"])
+
+
+@pytest.mark.parametrize("reduced", [False, True])
+@pytest.mark.parametrize("iters", [1, 20])
+def test_inertia_tensors_match_reference(reduced, iters):
+    g = _load("inertia_tensors")
+    some = False
+    for i in range(int(g["ten_n"])):
+        pos, w = g[f"ten{i}_pos"], g[f"ten{i}_w"]
+        t = oc.get_weighted_inertia_tensor(w, pos, 40.0, search_radius=1e4, reduced=reduced, max_iterations=iters)
+        t = np.zeros(6) if t is None else np.asarray(t, dtype=np.float64)
+        ref = g[f"ten{i}_3d_r{int(reduced)}_i{iters}"]
+        np.testing.assert_allclose(t, ref, rtol=1e-13, atol=0)
+        some |= bool(ref.any())
+        for axis in (0, 1, 2):
+            t = oc.get_weighted_projected_inertia_tensor(w, pos, axis, 40.0, reduced=reduced, max_iterations=iters)
+            t = np.zeros(3) if t is None else np.asarray(t, dtype=np.float64)
+            np.testing.assert_allclose(t, g[f"ten{i}_2d_a{axis}_r{int(reduced)}_i{iters}"], rtol=1e-13, atol=0)
+    assert some
+
+
+def test_shared_mesh_matches_reference():
+    g = _load("shared_mesh")
+    L = float(g["mesh_L"])
+    for i in range(int(g["mesh_n"])):
+        pos, res = g[f"mesh{i}_pos"], int(g[f"mesh{i}_res"])
+        mesh = om.MeshOracle(pos, res)
+        assert np.array_equal(mesh.pos_min, g[f"mesh{i}_pos_min"])
+        assert np.array_equal(mesh.pos_max, g[f"mesh{i}_pos_max"])
+        assert np.array_equal(mesh.cell_size, g[f"mesh{i}_cell_size"])
+        assert np.array_equal(mesh.cell_count, g[f"mesh{i}_cell_count"])
+        assert np.array_equal(mesh.cell_offset, g[f"mesh{i}_cell_offset"])
+        # within-cell order is unpinned by the reference: compare per-cell sets
+        so, ro = mesh.sort_idx, g[f"mesh{i}_sort_idx"]
+        assert np.array_equal(np.sort(so), np.sort(ro))
+        assert np.array_equal(mesh.cell_idx[so], mesh.cell_idx[ro])
+        for q in range(len(g[f"mesh{i}_radii"])):
+            c, r = g[f"mesh{i}_centres"][q], float(g[f"mesh{i}_radii"][q])
+            idx = np.sort(mesh.query_radius_periodic(c, r, pos, L))
+            assert np.array_equal(idx, g[f"mesh{i}_q{q}"]), f"mesh {i} query {q}"
+            # tests/test_shared_mesh.py:95-125: same set as brute force
+            assert np.array_equal(idx, np.sort(om.brute_force_query(pos, c, r, L)))
