@@ -54,6 +54,7 @@ ALG_BYTES = {
     "sort": 32,      # per record: 16 B in + 16 B out
     "scan_solve": 16,  # per record (one read of the sorted profile)
     "moments": 48,   # per pair: position 24, mass 4, velocity 12, grnr 4, fof 4
+    "small_halos": 48,  # fused tiers (small.cu), per pair: the whole stage B+C figure of SURVEY.md 8(d)
 }
 
 
@@ -423,6 +424,7 @@ def main():
         "sort": (stats.get("try_pairs", 0.0), ph.get("halos/sort", 0.0)),
         "scan_solve": (stats.get("try_pairs", 0.0), ph.get("halos/scan_solve", 0.0)),
         "moments": (stats.get("moment_pairs", 0.0), ph.get("halos/moments", 0.0)),
+        "small_halos": (stats.get("small_pairs", 0.0), sum(ph.get(f"halos/small_{t}", 0.0) for t in range(3))),
     }
     kernels = {}
     for k, (n_units, t_ms) in units.items():
@@ -471,7 +473,8 @@ def main():
             "algorithmic_gbs_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9 / peak, 4),
             "kernel_ms_per_step": round(kern_ms, 3),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "phases_ms": {k: round(v, 4) for k, v in sorted(ph.items())},
+            "stats": {k: int(v) for k, v in sorted(stats.items())}, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)

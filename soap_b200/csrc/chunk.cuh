@@ -62,6 +62,7 @@ struct soap_chunk {
     std::vector<void*> owned;  // device allocations freed at destroy
     uint32_t* orig = nullptr;  // [n] index within the particle's own ptype array
     int64_t last_pairs = 0;
+    int64_t last_small_pairs = 0;  // of which handled by the fused small-halo tiers
     int64_t last_candidates = 0;
     int64_t last_count_pairs = 0, last_try_pairs = 0, last_mom_pairs = 0;
     int last_rounds = 0;

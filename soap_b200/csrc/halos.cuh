@@ -142,7 +142,37 @@ struct Item {
 constexpr uint32_t ITEM_CAND = 16384;  // candidates per item
 constexpr int SWEEP_NT = 256;          // threads of every sweeping kernel = rows per batch
 
+// device counters of one round
+struct Counters {
+    unsigned int n_try, n_big, n_next, n_multi, n_fine;
+    unsigned long long rec_single, rec_total;
+    unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
+    unsigned int n_mslot, items_overflow;
+    unsigned long long pairs, candidates, count_pairs, mom_pairs;
+};
+
 #ifdef __CUDACC__
+// ------------------------------------------------------------------ ladder
+// halo_tasks.py:166-187 and :390-402.  Returns true if the halo stays pending.
+__device__ inline bool ladder_step(const HaloArrays& ha, uint32_t h, double required) {
+    const double search_radius = ha.sr_in[h], read_radius = ha.rr_in[h];
+    double cur = ha.cur_r[h];
+    double* row = ha.out + (int64_t)h * ha.ncol;
+    if (required > read_radius || cur >= read_radius) {
+        double sr = required > read_radius ? fmax(search_radius, required) : fmax(search_radius, cur);
+        row[4] = sr;                                        // halo_tasks.py:173,179
+        row[5] = fmax(__dmul_rn(read_radius, 1.5), sr);     // halo_tasks.py:393-396
+        ha.status[h] = SOAP_HALO_RADIUS_TOO_SMALL;
+        ha.state[h] = ST_DONE_FAIL;
+        return false;
+    }
+    cur = fmin(__dmul_rn(cur, 1.2), read_radius);  // halo_tasks.py:184-186
+    cur = fmax(cur, required);                      // halo_tasks.py:187
+    ha.cur_r[h] = cur;
+    ha.state[h] = ST_PENDING;
+    return true;
+}
+
 __device__ __forceinline__ int range_total(const DimRanges& r) {
     int t = 0;
     for (int a = 0; a < r.n; a++) t += r.hi[a] - r.lo[a] + 1;
@@ -180,9 +210,8 @@ __device__ __forceinline__ void row_span(const ChunkView& v, const DimRanges* rg
     s1 = v.cell_off[c1 + 1];
 }
 __device__ __forceinline__ void halo_ranges(const ChunkView& v, double cx, double cy, double cz,
-                                            double r, DimRanges* rg) {
-    // called by threads 0..2
-    int d = threadIdx.x;
+                                            double r, DimRanges* rg, int d) {
+    // called by three threads, one per dimension d
     double c = d == 0 ? cx : (d == 1 ? cy : cz);
     dim_ranges(c, r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
 }
@@ -210,7 +239,7 @@ __device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx,
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long a = im.first, b = (unsigned long long)im.first + im.count;
     __syncthreads();
-    if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, r, S.rg);
+    if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, r, S.rg, threadIdx.x);
     __syncthreads();
     const RowIter ri = row_iter(S.rg);
     int row_base = (int)im.row0;
@@ -264,5 +293,18 @@ __device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx,
         __syncthreads();
         if (row_base >= ri.nrows || pos_base >= b) break;
     }
+}
+// ----------------------------------------------------------- record helper
+struct Part {
+    double x, y, z, r;
+};
+__device__ __forceinline__ Part rel_part(const ChunkView& v, uint32_t t, double cx, double cy,
+                                         double cz, double halfL) {
+    Part p;
+    p.x = rewrap_rel(v.px[t], cx, v.L, halfL);
+    p.y = rewrap_rel(v.py[t], cy, v.L, halfL);
+    p.z = rewrap_rel(v.pz[t], cz, v.L, halfL);
+    p.r = radius3(p.x, p.y, p.z);
+    return p;
 }
 #endif
