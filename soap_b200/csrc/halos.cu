@@ -18,6 +18,8 @@
 //   k_moments      (moments.cu) masked moment sums + result row
 #include "scan.cuh"
 
+#include <stdlib.h>
+
 int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
                         const unsigned int* n_items_dev, unsigned int n_items_host,
                         unsigned int n_mslot, unsigned int grid, cudaStream_t stream);
@@ -77,12 +79,21 @@ __global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_t* lis
 __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
                                                     const unsigned int* __restrict__ n_pend,
                                                     Item* __restrict__ items, unsigned int items_cap,
-                                                    Counters* ctr) {
+                                                    Counters* ctr, int look, int replan) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_pend) return;
     const uint32_t h = pend[it];
     DimRanges rg[3];
-    const double r = ha.cur_r[h];
+    // round start: plan the sweep of the furthest of the next `look` ladder rungs;
+    // replan: the sweep of the accepted rung (collect / moments)
+    double r = ha.cur_r[h];
+    if (!replan) {
+        double rr[LOOK_MAX];
+        const int nr = ladder_radii(r, ha.rr_in[h], look, rr);
+        ha.look[h] = nr;
+        r = rr[nr - 1];
+        for (int k = 0; k < LOOK_MAX; k++) { ha.rung_cnt[(size_t)h * LOOK_MAX + k] = 0; ha.rung_msum[(size_t)h * LOOK_MAX + k] = 0.0; }
+    }
     for (int d = 0; d < 3; d++)
         dim_ranges(ha.cofp[3 * h + d], r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
     const RowIter ri = row_iter(rg);
@@ -103,12 +114,13 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
     }
     ha.item_base[h] = base;
     ha.n_items[h] = ni;
-    ha.cnt[h] = 0;
-    ha.msum[h] = 0.0;
-    ha.rung_r[h] = r;
     ha.cursor[h] = 0;
     ha.items_done[h] = 0;
-    ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+    if (!replan) {
+        ha.cnt[h] = 0;
+        ha.msum[h] = 0.0;
+        ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+    }
     ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
     if (ni == 1) {
         Item im;
@@ -138,72 +150,104 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
             pos = end;
         }
     }
-    atomicAdd(&ctr->candidates, cand);
+    if (!replan) atomicAdd(&ctr->candidates, cand);
 }
 
 // ----------------------------------------------------------------- k_count
-// periodic sphere count + enclosed mass of every pending halo at its current
-// radius (halo_tasks.py:84-97; shared_mesh.py:122-200)
+// periodic sphere count + enclosed mass of every pending halo (halo_tasks.py:84-97;
+// shared_mesh.py:122-200), for the next ha.look[h] ladder rungs in one sweep:
+// the sphere of the furthest rung is swept once and every particle is binned by
+// the first rung whose radius includes it (the same r2 <= radius^2 test).
 __global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
                                               Counters* ctr) {
     __shared__ SweepShared S;
-    __shared__ unsigned long long s_cnt[TB / 32];
-    __shared__ double s_m[TB / 32];
+    __shared__ unsigned int s_cnt[TB / 32][LOOK_MAX];
+    __shared__ double s_m[TB / 32][LOOK_MAX];
     const unsigned int n_items = ctr->n_items;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const Item im = items[it];
         const uint32_t h = im.halo;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
-        const double r = ha.cur_r[h];
-        const double r2max = __dmul_rn(r, r);
+        double rr[LOOK_MAX], r2k[LOOK_MAX];
+        const int nr = ladder_radii(ha.cur_r[h], ha.rr_in[h], ha.look[h], rr);
+#pragma unroll
+        for (int k = 0; k < LOOK_MAX; k++) r2k[k] = k < nr ? __dmul_rn(rr[k], rr[k]) : -1.0;
+        const double r = rr[nr - 1];
         const double halfL = 0.5 * v.L, L = v.L;
-        unsigned long long cnt = 0;
-        double msum = 0.0;
+        unsigned int cnt[LOOK_MAX];
+        double msum[LOOK_MAX];
+#pragma unroll
+        for (int k = 0; k < LOOK_MAX; k++) { cnt[k] = 0; msum[k] = 0.0; }
         sweep_item(v, S, cx, cy, cz, r, im, [&](uint32_t t, bool ok) {
             if (ok) {
-                double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
-                if (r2 <= r2max) {
-                    cnt++;
-                    msum += (double)v.mass[t];
+                const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+                if (r2 <= r2k[nr - 1]) {
+                    const double m = (double)v.mass[t];
+                    bool placed = false;
+#pragma unroll
+                    for (int k = 0; k < LOOK_MAX; k++)
+                        if (!placed && k < nr && r2 <= r2k[k]) { cnt[k]++; msum[k] += m; placed = true; }
                 }
             }
         });
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        cnt = warp_sum_u64(cnt);
-        msum = warp_sum(msum);
-        if (lane == 0) { s_cnt[wid] = cnt; s_m[wid] = msum; }
+#pragma unroll
+        for (int k = 0; k < LOOK_MAX; k++) {
+            const unsigned int c = (unsigned int)warp_sum_u64(cnt[k]);
+            const double m = warp_sum(msum[k]);
+            if (lane == 0) { s_cnt[wid][k] = c; s_m[wid][k] = m; }
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long c = 0;
+        if (threadIdx.x < (unsigned)nr) {
+            const int k = threadIdx.x;
+            unsigned int c = 0;
             double m = 0.0;
-            for (int w = 0; w < TB / 32; w++) { c += s_cnt[w]; m += s_m[w]; }
-            if (c) atomicAdd(&ha.cnt[h], (unsigned int)c);
-            if (m != 0.0) atomicAdd(&ha.msum[h], m);
-            atomicAdd(&ctr->count_pairs, c);
+            for (int w = 0; w < TB / 32; w++) { c += s_cnt[w][k]; m += s_m[w][k]; }
+            if (c) atomicAdd(&ha.rung_cnt[(size_t)h * LOOK_MAX + k], c);
+            if (m != 0.0) atomicAdd(&ha.rung_msum[(size_t)h * LOOK_MAX + k], m);
+            atomicAdd(&ctr->count_pairs, (unsigned long long)c);
         }
         __syncthreads();
     }
 }
 
-
 __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ pend,
                                               const unsigned int* __restrict__ n_pend,
                                               uint32_t* __restrict__ try_list,
                                               uint32_t* __restrict__ big_list,
+                                              uint32_t* __restrict__ acc_list,
                                               uint32_t* __restrict__ multi_list,
                                               uint32_t* __restrict__ next, Counters* ctr) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_pend) return;
     const uint32_t h = pend[it];
-    ha.nloop[h] += 1;  // halo_tasks.py:75
-    const double r = ha.cur_r[h];
-    // halo_tasks.py:97
-    const double density = ha.msum[h] / (4.0 / 3.0 * SOAP_PI * (r * r * r));
+    // walk the rungs covered by this round's sweep (halo_tasks.py:73-103,166-187)
+    const int nr = ha.look[h];
     const bool has_target = ha.central[h] == 1 && cfg.target_density > 0.0;  // halo_tasks.py:381
-    if (!has_target || density <= cfg.target_density) {  // halo_tasks.py:103
+    unsigned int ccum = 0;
+    double mcum = 0.0;
+    bool accepted = false, pending = true;
+    for (int k = 0; k < nr && pending; k++) {
+        ha.nloop[h] += 1;  // halo_tasks.py:75
+        const double r = ha.cur_r[h];
+        ccum += ha.rung_cnt[(size_t)h * LOOK_MAX + k];
+        mcum += ha.rung_msum[(size_t)h * LOOK_MAX + k];
+        // halo_tasks.py:97
+        const double density = mcum / (4.0 / 3.0 * SOAP_PI * (r * r * r));
+        if (!has_target || density <= cfg.target_density) {  // halo_tasks.py:103
+            accepted = true;
+            break;
+        }
+        pending = ladder_step(ha, h, 0.0);  // next rung, or out of read radius
+    }
+    if (accepted) {
+        ha.cnt[h] = ccum;
+        ha.msum[h] = mcum;
+        ha.rung_r[h] = ha.cur_r[h];
         const uint32_t cnt = ha.cnt[h];
         if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // scanned by a CTA cluster
         else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
+        acc_list[atomicAdd(&ctr->n_acc, 1u)] = h;  // every accepted halo: its sweep is planned again
         ha.state[h] = ST_TRY;
         if (cnt <= SB_CAP) {
             ha.rec_off[h] = atomicAdd(&ctr->rec_single, (unsigned long long)cnt);
@@ -217,8 +261,8 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
             multi_list[atomicAdd(&ctr->n_multi, 1u)] = h;
         }
         atomicAdd(&ctr->rec_total, (unsigned long long)cnt);
-    } else {
-        if (ladder_step(ha, h, 0.0)) next[atomicAdd(&ctr->n_next, 1u)] = h;
+    } else if (pending) {
+        next[atomicAdd(&ctr->n_next, 1u)] = h;
     }
 }
 
@@ -564,6 +608,10 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(listB, uint32_t, h, "h_listB", H);
     WS_GET(try_list, uint32_t, h, "h_try", H);
     WS_GET(big_list, uint32_t, h, "h_big", H);
+    WS_GET(acc_list, uint32_t, h, "h_acc", H);
+    WS_GET(look_arr, int32_t, h, "h_look", H); ha.look = look_arr;
+    WS_GET(rung_cnt, uint32_t, h, "h_rung_cnt", (size_t)H * LOOK_MAX); ha.rung_cnt = rung_cnt;
+    WS_GET(rung_msum, double, h, "h_rung_msum", (size_t)H * LOOK_MAX); ha.rung_msum = rung_msum;
     WS_GET(multi_list, uint32_t, h, "h_multi", H);
     WS_GET(ctr, Counters, h, "h_ctr", 8);  // [0] current round, [2..4] the fused tiers
     WS_GET(n_pend_dev, unsigned int, h, "h_npend", 4);
@@ -633,47 +681,62 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += small_ctr[t].candidates;
     }
     c->last_small_pairs = (int64_t)total_pairs;
+    const bool trace = getenv("SOAP_B200_TRACE") != nullptr;
+    if (trace)
+        fprintf(stderr, "[soap_b200] tiers: lists %u %u %u -> general %u | small pairs %llu %llu %llu\n", 0u, 0u, 0u, n_pend,
+                (unsigned long long)small_ctr[0].pairs, (unsigned long long)small_ctr[1].pairs, (unsigned long long)small_ctr[2].pairs);
     while (n_pend > 0) {
         c->last_rounds++;
         if (c->last_rounds > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
         CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
-        log.begin("plan", stream);
-        LAUNCH(h, k_plan_items, grid_for(n_pend, 128), 128, 0, stream, v, ha, pend, n_pend_dev, items,
-               (unsigned int)items_cap, ctr);
-        log.end(stream);
-        {
-            // coarse meshes / huge spheres can need more work items than provisioned
-            Counters pc;
-            CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            if (pc.items_overflow) {
-                if (pc.n_items >= 0xfff00000u) SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", pc.n_items);
+        // ladder look-ahead: the first round covers 4 rungs per sweep, stragglers more
+        const int look = c->last_rounds == 1 ? 4 : (c->last_rounds == 2 ? 6 : LOOK_MAX);
+        // plan a sweep per halo of `list`; coarse meshes / huge spheres can need more
+        // work items than provisioned: grow the list and plan again
+        auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int replan) -> int {
+            for (int attempt = 0; attempt < 2; attempt++) {
+                CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 3 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow
+                LAUNCH(h, k_plan_items, grid_for(n_host, 128), 128, 0, stream, v, ha, list, n_dev, items,
+                       (unsigned int)items_cap, ctr, look, replan);
+                Counters pc;
+                CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                if (!pc.items_overflow) return 0;
+                if (attempt == 1 || pc.n_items >= 0xfff00000u)
+                    SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", pc.n_items);
                 items_cap = (size_t)pc.n_items + 1024;
                 items = (Item*)h->get("h_items", sizeof(Item) * items_cap);
                 item_minr = (unsigned long long*)h->get("h_item_minr", sizeof(unsigned long long) * items_cap);
                 item_minfof = (int32_t*)h->get("h_item_minfof", sizeof(int32_t) * items_cap);
                 if (!items || !item_minr || !item_minfof) return -1;
-                CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
-                LAUNCH(h, k_plan_items, grid_for(n_pend, 128), 128, 0, stream, v, ha, pend, n_pend_dev, items,
-                       (unsigned int)items_cap, ctr);
+                if (!replan) CUDA_TRY(cudaMemsetAsync(&ctr->candidates, 0, sizeof(unsigned long long), stream));
             }
-        }
+            return 0;
+        };
+        log.begin("plan", stream);
+        if (plan(pend, n_pend_dev, n_pend, 0)) return -1;
+        log.end(stream);
         log.begin("count", stream);
         LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr);
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
-               multi_list, next, ctr);
+               acc_list, multi_list, next, ctr);
         log.end(stream);
         Counters hc;
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        if (hc.items_overflow) SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", hc.n_items);
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
         if (hc.n_try + hc.n_big > 0) {
             const unsigned int n_try = hc.n_try + hc.n_big;
+            // the accepted radius is generally smaller than the swept one: plan its sweep
+            log.begin("plan", stream);
+            if (plan(acc_list, &ctr->n_acc, n_try, 1)) return -1;
+            log.end(stream);
+            CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
             // workspace for this round
             Rec* recs = (Rec*)h->get("h_recs", sizeof(Rec) * (size_t)(hc.rec_total + 1));
             if (!recs) return -1;
@@ -748,6 +811,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         CUDA_TRY(cudaStreamSynchronize(stream));
         total_pairs += hc2.pairs;
         total_mom_pairs += hc2.mom_pairs;
+        if (trace)
+            fprintf(stderr, "[soap_b200] round %d: pend %u items %u cand %llu in-sphere %llu | try %u big %u multi %u recs %llu | final-pairs %llu next %u\n",
+                    c->last_rounds, n_pend, hc.n_items, (unsigned long long)hc.candidates,
+                    (unsigned long long)hc.count_pairs, hc.n_try, hc.n_big, hc.n_multi,
+                    (unsigned long long)hc.rec_total, (unsigned long long)hc2.pairs, hc2.n_next);
         n_pend = hc2.n_next;
         uint32_t* t = pend; pend = next; next = t;
     }

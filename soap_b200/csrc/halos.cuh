@@ -129,7 +129,13 @@ struct HaloArrays {
     unsigned int* cursor;      // append cursor of single-bucket halos (k_collect)
     unsigned int* items_done;  // last-arriver counter (k_moments)
     int32_t* mslot;            // global bank slot of multi-item halos, -1 otherwise
+    // ladder look-ahead: one count sweep bins the sphere of the furthest rung by rung
+    int32_t* look;             // rungs covered by this round's sweep (1..LOOK_MAX)
+    uint32_t* rung_cnt;        // [H][LOOK_MAX] particles first included at rung k
+    double* rung_msum;         // [H][LOOK_MAX] their mass
 };
+
+constexpr int LOOK_MAX = 8;  // ladder rungs one count sweep can cover
 
 // A work item = a contiguous range [first, first+count) of a halo's candidate
 // stream (its rows concatenated in row order).  row0 / pos0 locate the first
@@ -144,7 +150,7 @@ constexpr int SWEEP_NT = 256;          // threads of every sweeping kernel = row
 
 // device counters of one round
 struct Counters {
-    unsigned int n_try, n_big, n_next, n_multi, n_fine;
+    unsigned int n_try, n_big, n_acc, n_next, n_multi, n_fine;
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
     unsigned int n_mslot, items_overflow;
@@ -171,6 +177,19 @@ __device__ inline bool ladder_step(const HaloArrays& ha, uint32_t h, double requ
     ha.cur_r[h] = cur;
     ha.state[h] = ST_PENDING;
     return true;
+}
+
+// Radii of the next rungs of the ladder starting at cur, exactly as repeated
+// gate failures would produce them (halo_tasks.py:184-187 with required = 0):
+// r[k+1] = min(1.2 r[k], read_radius).  Stops at read_radius; returns the count.
+__device__ __forceinline__ int ladder_radii(double cur, double read_radius, int kmax, double* r) {
+    int n = 1;
+    r[0] = cur;
+    while (n < kmax && r[n - 1] < read_radius) {
+        r[n] = fmin(__dmul_rn(r[n - 1], 1.2), read_radius);
+        n++;
+    }
+    return n;
 }
 
 __device__ __forceinline__ int range_total(const DimRanges& r) {
