@@ -34,7 +34,7 @@ namespace {
 constexpr int TB = SWEEP_NT;
 constexpr int SB_CAP = 4096;     // records of one bucket sorted in shared memory (64 KB)
 constexpr int SMALL_CAP = 512;   // small-bucket class (8 KB)
-constexpr int FINE_TARGET = 128; // expected records per fine radial bin
+constexpr int FINE_TARGET = 8;   // expected records per fine radial bin (sorted by one warp in registers)
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
 // halos with up to this many bound particles start in fused tier 0 / 1 / 2; larger ones take the general path
@@ -249,13 +249,13 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
         else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
         acc_list[atomicAdd(&ctr->n_acc, 1u)] = h;  // every accepted halo: its sweep is planned again
         ha.state[h] = ST_TRY;
-        if (cnt <= SB_CAP) {
+        if (cnt <= SMALL_CAP) {
             ha.rec_off[h] = atomicAdd(&ctr->rec_single, (unsigned long long)cnt);
             ha.nfine[h] = 0;
         } else {
             uint32_t nf = cnt / FINE_TARGET;
             if (nf < 64) nf = 64;
-            if (nf > 65536) nf = 65536;
+            if (nf > (1u << 22)) nf = 1u << 22;
             ha.nfine[h] = nf;
             ha.fine_off[h] = atomicAdd(&ctr->n_fine, nf);
             multi_list[atomicAdd(&ctr->n_multi, 1u)] = h;
@@ -299,40 +299,83 @@ __global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays h
     }
 }
 
-// Group a multi-bucket halo's fine radial bins into sort buckets: bins whose
-// first record falls into the same BKT_SPAN-wide window of the halo's record
-// range form one bucket (one CTA per halo, one thread per bin; a bin starts a
-// bucket if its window differs from its predecessor's).  A bucket holds at
-// most BKT_SPAN - 1 records plus its last bin.
-constexpr uint32_t BKT_SPAN = SB_CAP / 2;
-__global__ void __launch_bounds__(256) k_build_buckets(HaloArrays ha, const uint32_t* __restrict__ multi_list,
-                                                       const int64_t* __restrict__ fine_excl, Counters* ctr,
-                                                       Bucket* __restrict__ bkt_small, Bucket* __restrict__ bkt_big,
-                                                       Bucket* __restrict__ bkt_huge) {
-    const uint32_t h = multi_list[blockIdx.x];
-    const uint32_t nf = ha.nfine[h], fo = ha.fine_off[h];
+// Radial sort of the multi-bin halos: their records were scattered into fine
+// radial bins of ~FINE_TARGET records by k_collect, so the stream is already
+// ordered at bin granularity and every bin is sorted on its own.  One warp per
+// bin: up to 32 records in registers (bitonic network over shuffles, no shared
+// memory, no barriers), up to BIN_SMEM in the warp's shared-memory slice; the
+// rare larger bins become buckets of the CTA-wide sort kernels.
+constexpr int BIN_SMEM = 256;
+__global__ void __launch_bounds__(256) k_sort_bins(const int64_t* __restrict__ fine_excl, uint32_t n_fine,
+                                                   Counters* ctr, Rec* __restrict__ recs,
+                                                   Bucket* __restrict__ bkt_big, Bucket* __restrict__ bkt_huge) {
+    __shared__ Rec sm[8][BIN_SMEM];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long base = ctr->rec_single;  // multi region follows the single region
-    const unsigned long long e0 = (unsigned long long)fine_excl[fo];
-    if (threadIdx.x == 0) ha.rec_off[h] = base + e0;
-    const unsigned long long e_end = e0 + ha.cnt[h];
-    for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x) {
-        const unsigned long long ef = (unsigned long long)fine_excl[fo + f];
-        const unsigned long long gf = (ef - e0) / BKT_SPAN;
-        if (f > 0 && ((unsigned long long)fine_excl[fo + f - 1] - e0) / BKT_SPAN == gf) continue;
-        // bucket start: find the first later bin in another window
-        uint32_t f2 = f + 1;
-        while (f2 < nf && ((unsigned long long)fine_excl[fo + f2] - e0) / BKT_SPAN == gf) f2++;
-        const unsigned long long e2 = f2 < nf ? (unsigned long long)fine_excl[fo + f2] : e_end;
-        const unsigned long long c = e2 - ef;
-        if (c == 0) continue;
-        Bucket b;
-        b.start = base + ef;
-        b.count = (uint32_t)c;
-        b.halo = h;
-        if (c <= SMALL_CAP) bkt_small[atomicAdd(&ctr->n_bkt_small, 1u)] = b;
-        else if (c <= SB_CAP) bkt_big[atomicAdd(&ctr->n_bkt_big, 1u)] = b;
-        else bkt_huge[atomicAdd(&ctr->n_bkt_huge, 1u)] = b;
+    const uint32_t nwarp = gridDim.x * 8;
+    for (uint32_t b = blockIdx.x * 8 + wid; b < n_fine; b += nwarp) {
+        const unsigned long long e0 = (unsigned long long)fine_excl[b];
+        const uint32_t cnt = (uint32_t)((unsigned long long)fine_excl[b + 1] - e0);
+        if (cnt < 2) continue;
+        Rec* g = recs + base + e0;
+        if (cnt <= 32) {
+            Rec mine;
+            if (lane < (int)cnt) mine = g[lane];
+            else { mine.rbits = ~0ull; mine.m = 0.f; mine.flags = 0; }
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    Rec o;
+                    o.rbits = __shfl_xor_sync(0xffffffffu, mine.rbits, j);
+                    o.m = __shfl_xor_sync(0xffffffffu, mine.m, j);
+                    o.flags = __shfl_xor_sync(0xffffffffu, mine.flags, j);
+                    const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+                    if (take_min ? (o.rbits < mine.rbits) : (mine.rbits < o.rbits)) mine = o;
+                }
+            }
+            if (lane < (int)cnt) g[lane] = mine;
+        } else if (cnt <= BIN_SMEM) {
+            Rec* s = sm[wid];
+            for (uint32_t t = lane; t < cnt; t += 32) s[t] = g[t];
+            __syncwarp();
+            uint32_t np2 = 64;
+            while (np2 < cnt) np2 <<= 1;
+            auto cx = [&](uint32_t t, uint32_t p) {
+                if (p > t && p < cnt) {
+                    const Rec x = s[t], y = s[p];
+                    if (y.rbits < x.rbits) { s[t] = y; s[p] = x; }
+                }
+            };
+            for (uint32_t k = 2; k <= np2; k <<= 1) {
+                for (uint32_t t = lane; t < np2; t += 32) cx(t, t ^ (k - 1));
+                __syncwarp();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t t = lane; t < np2; t += 32) cx(t, t ^ j);
+                    __syncwarp();
+                }
+            }
+            for (uint32_t t = lane; t < cnt; t += 32) g[t] = s[t];
+            __syncwarp();
+        } else if (lane == 0) {
+            Bucket bk;
+            bk.start = base + e0;
+            bk.count = cnt;
+            bk.halo = 0;
+            if (cnt <= SB_CAP) bkt_big[atomicAdd(&ctr->n_bkt_big, 1u)] = bk;
+            else bkt_huge[atomicAdd(&ctr->n_bkt_huge, 1u)] = bk;
+        }
     }
+}
+
+// rec_off of the multi-bin halos (their bins are contiguous in the bin table)
+__global__ void k_multi_offsets(HaloArrays ha, const uint32_t* __restrict__ multi_list,
+                                const unsigned int* __restrict__ n_multi,
+                                const int64_t* __restrict__ fine_excl, const Counters* __restrict__ ctr) {
+    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_multi) return;
+    const uint32_t h = multi_list[it];
+    ha.rec_off[h] = ctr->rec_single + (unsigned long long)fine_excl[ha.fine_off[h]];
 }
 
 // single-bucket halos -> bucket lists (thread per try halo)
@@ -460,7 +503,7 @@ __global__ void __launch_bounds__(NT) k_sort_bucket(const Bucket* __restrict__ b
 // One CTA (CS == 1) or one cluster of CS CTAs (halos above SCAN_BIG records)
 // per halo of the list; the per-halo work is scan_solve_halo (scan.cuh).
 template <int NCH, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ? 2 : 1)
     k_scan_solve(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ try_list,
                  const unsigned int* __restrict__ n_try, const Rec* __restrict__ recs,
                  uint32_t* __restrict__ next, Counters* ctr,
@@ -740,10 +783,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             // workspace for this round
             Rec* recs = (Rec*)h->get("h_recs", sizeof(Rec) * (size_t)(hc.rec_total + 1));
             if (!recs) return -1;
-            size_t max_bkt = (size_t)n_try + (size_t)(hc.rec_total / 16) + hc.n_fine + 16;
+            // single-bin halos give one bucket each; bins above BIN_SMEM records (k_sort_bins) one each
+            const size_t max_bkt = (size_t)n_try + (size_t)(hc.rec_total / BIN_SMEM) + 16;
             Bucket* bkt_small = (Bucket*)h->get("h_bkt_small", sizeof(Bucket) * max_bkt);
             Bucket* bkt_big = (Bucket*)h->get("h_bkt_big", sizeof(Bucket) * max_bkt);
-            Bucket* bkt_huge = (Bucket*)h->get("h_bkt_huge", sizeof(Bucket) * (size_t)(hc.n_multi + hc.n_fine + 16));
+            Bucket* bkt_huge = (Bucket*)h->get("h_bkt_huge", sizeof(Bucket) * (size_t)(hc.rec_total / SB_CAP + 16));
             uint32_t* fine_cnt = (uint32_t*)h->get("h_fine_cnt", sizeof(uint32_t) * (size_t)(hc.n_fine + 1));
             uint32_t* fine_cur = (uint32_t*)h->get("h_fine_cur", sizeof(uint32_t) * (size_t)(hc.n_fine + 1));
             int64_t* fine_excl = (int64_t*)h->get("h_fine_excl", sizeof(int64_t) * (size_t)(hc.n_fine + 1));
@@ -755,8 +799,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                 CUDA_TRY(cudaMemsetAsync(fine_cur, 0, sizeof(uint32_t) * (hc.n_fine + 1), stream));
                 LAUNCH(h, k_fine_hist_halo, sweep_grid, TB, 0, stream, v, ha, items, ctr, fine_cnt);
                 if (soap_exclusive_scan_u32(h, fine_cnt, nullptr, fine_excl, hc.n_fine + 1, nullptr, stream)) return -1;
-                LAUNCH(h, k_build_buckets, hc.n_multi, 256, 0, stream, ha, multi_list, fine_excl, ctr, bkt_small,
-                       bkt_big, bkt_huge);
+                LAUNCH(h, k_multi_offsets, grid_for(hc.n_multi, 128), 128, 0, stream, ha, multi_list, &ctr->n_multi,
+                       fine_excl, ctr);
                 log.end(stream);
             }
             if (hc.n_try > 0)
@@ -767,6 +811,12 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                    item_minr, item_minfof);
             log.end(stream);
             log.begin("sort", stream);
+            if (hc.n_multi > 0) {
+                // bins first: they feed the bucket lists of the CTA-wide kernels below
+                const unsigned int nb = (hc.n_fine + 7) / 8;
+                LAUNCH(h, k_sort_bins, nb < (unsigned)(sm * 8) ? nb : (unsigned)(sm * 8), 256, 0, stream, fine_excl,
+                       hc.n_fine, ctr, recs, bkt_big, bkt_huge);
+            }
             {
                 unsigned int gs = (unsigned)(max_bkt < (size_t)(sm * 16) ? max_bkt : (size_t)(sm * 16));
                 LAUNCH(h, (k_sort_bucket<SMALL_CAP, 128>), gs, 128, SMALL_CAP * sizeof(Rec), stream, bkt_small,
