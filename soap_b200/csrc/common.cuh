@@ -105,7 +105,7 @@ static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {
 
 // numpy floored modulo for positive divisor L (npy_divmod): fmod, then shift
 // negative remainders by L (the sum is rounded, so tiny negatives give L).
-__device__ __forceinline__ double floored_mod(double a, double L) {
+static __device__ __noinline__ double floored_mod_generic(double a, double L) {
     double m = fmod(a, L);
     if (m != 0.0) {
         if (m < 0.0) m = __dadd_rn(m, L);
@@ -113,6 +113,14 @@ __device__ __forceinline__ double floored_mod(double a, double L) {
         m = 0.0;  // copysign(0, L) with L > 0
     }
     return m;
+}
+__device__ __forceinline__ double floored_mod(double a, double L) {
+    // fast paths, bit-identical to the generic branch: for |a| < L fmod returns a
+    // itself, and for L <= a < 2L it returns a - L, which is exact (Sterbenz)
+    if (a > 0.0 && a < L) return a;
+    if (a < 0.0 && a > -L) return __dadd_rn(a, L);
+    if (a >= L && a < __dadd_rn(L, L)) return __dsub_rn(a, L);
+    return floored_mod_generic(a, L);
 }
 
 // periodic minimum-image displacement of SharedMesh.query_radius_periodic

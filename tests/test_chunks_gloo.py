@@ -1,0 +1,113 @@
+"""Host logic of the multi-GPU path (soap_b200/chunk_tasks.py) on CPU: Peano
+decomposition, ghost shells, chunk -> rank mapping and the result gather, run
+with torch.distributed (gloo) at world_size 2.  The per-chunk compute is the
+oracle's periodic sphere count (no GPU here): a chunk carrying its own ghost
+shell must give exactly the whole-box answer for each of its halos."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import mesh as om
+from soap_b200 import chunk_tasks as ct
+
+L = 50.0
+
+
+def _box(seed=5, n=40000, nh=60):
+    rng = np.random.default_rng(seed)
+    pos = rng.random((n, 3)) * L
+    cofp = rng.random((nh, 3)) * L
+    cofp[:6] = np.array([[0.1, 0.2, 49.9], [49.8, 25.0, 0.05], [25.0, 49.95, 25.0], [0.0, 0.0, 0.0], [49.99, 49.99, 49.99],
+                         [0.3, 49.7, 10.0]])  # halos straddling the periodic faces / corners
+    halo = {
+        "cofp": cofp,
+        "index": np.arange(nh, dtype=np.int64) * 3 + 7,
+        "search_radius": 0.5 + 2.0 * rng.random(nh),
+        "read_radius": np.full(nh, 3.0),
+    }
+    data = {1: {"Coordinates": pos, "Masses": rng.random(n).astype(np.float32)}}
+    return data, halo
+
+
+def _compute(cd, hc):
+    """count + enclosed mass inside search_radius, from the chunk's particles only"""
+    pos, m = cd[1]["Coordinates"], cd[1]["Masses"]
+    out = np.zeros((len(hc["index"]), 2))
+    for i in range(len(hc["index"])):
+        idx = om.brute_force_query(pos, hc["cofp"][i], hc["search_radius"][i], L)
+        out[i] = [len(idx), m[idx].astype(np.float64).sum()]
+    return torch.as_tensor(out)
+
+
+def _whole_box(data, halo):
+    return _compute(data, halo).numpy()
+
+
+def test_hilbert_keys_are_a_bijection_and_continuous():
+    bits = 3
+    g = np.arange(2**bits)
+    ix, iy, iz = [a.ravel() for a in np.meshgrid(g, g, g, indexing="ij")]
+    key = ct.hilbert_keys(ix, iy, iz, bits)
+    assert sorted(key.tolist()) == list(range(8**bits))
+    order = np.argsort(key)
+    steps = np.abs(np.diff(ix[order])) + np.abs(np.diff(iy[order])) + np.abs(np.diff(iz[order]))
+    assert np.all(steps == 1)  # consecutive cells of a Hilbert curve are face neighbours
+
+
+def test_decomposition_sizes_and_assignment():
+    _, halo = _box()
+    hs, cs = ct.peano_decomposition(L, halo, 8)
+    assert cs.sum() == 60 and cs.max() - cs.min() <= 1 and np.all(np.diff(cs) <= 0)
+    assert sorted(hs["index"].tolist()) == sorted(halo["index"].tolist())
+    _, cs1 = ct.peano_decomposition(L, halo, 1000)  # domain_decomposition.py:76-78
+    assert len(cs1) == 60
+    a = ct.assign_chunks(8, 3)
+    assert a == [[0, 3, 6], [1, 4, 7], [2, 5]]
+
+
+def test_single_process_chunks_equal_whole_box():
+    data, halo = _box()
+    t, i = ct.run_chunks(data, halo, L, 7, _compute)
+    order = np.argsort(halo["index"])
+    assert np.array_equal(i.numpy(), halo["index"][order])
+    assert np.array_equal(t.numpy(), _whole_box(data, halo)[order])
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data, halo = _box()
+        got = ct.run_chunks(data, halo, L, 7, _compute, rank=rank, world_size=world)
+        if rank == 0:
+            q.put((got[0].numpy(), got[1].numpy()))
+        else:
+            assert got is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_gather_equals_whole_box():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    t, i = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    data, halo = _box()
+    order = np.argsort(halo["index"])
+    assert np.array_equal(i, halo["index"][order])
+    assert np.array_equal(t, _whole_box(data, halo)[order])
