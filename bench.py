@@ -387,22 +387,38 @@ def main():
         del data
         torch.cuda.empty_cache()
 
-        def step_e2e():
-            ch = DeviceChunk(host, L, device=local_rank, fine_ppc=args.fine_ppc, handle=handle)
-            r = process_halos(ch, cfg, host_h, out=table)
-            out_host.copy_(r.table, non_blocking=True)
-            st = r.status.cpu()
-            torch.cuda.synchronize()
-            ch.free()
+        from soap_b200.halo_tasks import ChunkFeed
+
+        feed = ChunkFeed(local_rank)
+
+        def run_e2e(n):
+            """n chunks through the public API; chunk i+1's host->device copy is in flight
+            while chunk i is processed (every chunk is copied from pinned host memory and
+            its result table is read back inside the timed region)."""
+            if n <= 0:
+                return None
+            nxt = feed.upload(host, host_h)
+            st = None
+            for i in range(n):
+                cur = nxt
+                if i + 1 < n:
+                    nxt = feed.upload(host, host_h)
+                d_dev, h_dev = feed.wait(cur)
+                ch = DeviceChunk(d_dev, L, device=local_rank, fine_ppc=args.fine_ppc, handle=handle)
+                del d_dev
+                r = process_halos(ch, cfg, h_dev, out=table)
+                out_host.copy_(r.table, non_blocking=True)
+                st = r.status.cpu()
+                torch.cuda.synchronize()
+                ch.free()
+                del cur
             return st
 
-        for _ in range(min(args.warmup, 2)):
-            step_e2e()
+        run_e2e(min(args.warmup, 2))
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            step_e2e()
+        n_e2e = max(1, args.steps)
+        run_e2e(n_e2e)
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -410,7 +426,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": H * world / dt, "unit": "halos/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt,
+               "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i"}
 
     # -------------------------------------------------------- roofline (rank 0)
     peak, peak_kind = peak_hbm()

@@ -216,6 +216,44 @@ class DeviceChunk:
             pass
 
 
+class ChunkFeed:
+    """Asynchronous chunk feed: uploads the next chunk's particle and halo arrays
+    from pinned host memory on a copy stream while the current chunk is being
+    processed (the reference reads chunk k+1's cells while chunk k is in
+    ``process_halos`` only across nodes; within a node this is SURVEY.md 8(f) rank 3:
+    SOAP/core/chunk_tasks.py:194-288).  Host tensors must already have the device
+    dtypes (float64 positions, float32 masses / velocities, int32 or int64 ids)."""
+
+    def __init__(self, device=0):
+        import torch
+
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def upload(self, data_host, halos_host):
+        """Start the upload; returns a ticket for ``wait``."""
+        import torch
+
+        with torch.cuda.stream(self.stream):
+            data = {pt: {k: v.to(self.device, non_blocking=True) for k, v in d.items()} for pt, d in data_host.items()}
+            halos = {k: v.to(self.device, non_blocking=True) for k, v in halos_host.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return data, halos, ev
+
+    def wait(self, ticket):
+        """Make the current stream wait for the upload; returns (data, halos) on the device."""
+        import torch
+
+        data, halos, ev = ticket
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for d in list(data.values()) + [halos]:
+            for t in d.values():
+                t.record_stream(cur)
+        return data, halos
+
+
 class HaloResults:
     """Result table of ``process_halos``: one float64 row per halo."""
 
