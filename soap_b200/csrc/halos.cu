@@ -24,6 +24,10 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
                         const unsigned int* n_items_dev, unsigned int n_items_host,
                         unsigned int n_mslot, unsigned int grid, cudaStream_t stream);
 int soap_write_input_cols(soap_handle* h, const HaloArrays& ha, int64_t nh, cudaStream_t stream);
+int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
+                      const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* acc_list,
+                      const unsigned int* n_acc_dev, unsigned int n_acc_host, unsigned int grid,
+                      cudaStream_t stream);
 int soap_small_tier_fits(const DevCfg& cfg, int tier);
 int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int tier, const uint32_t* list,
                       const unsigned int* n_list, unsigned int n_list_upper, uint32_t* overflow,
@@ -687,7 +691,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     {
         long long prev = -1;
         for (int t = 0; t < NTIER; t++) {
-            tier_on[t] = soap_small_tier_fits(dc, t) != 0;
+            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo);
             tl.lim[t] = tier_on[t] ? tier_nexp[t] : prev;  // a disabled tier takes no halos
             prev = tl.lim[t];
         }
@@ -852,6 +856,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             log.end(stream);
             log.begin("moments", stream);
             if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
+            if (soap_launch_kappa(c, dc, ha, items, &ctr->n_items, hc.n_items, acc_list, &ctr->n_acc, n_try, sweep_grid,
+                                  stream))
+                return -1;
             log.end(stream);
         }
         // next round's pending list

@@ -125,6 +125,162 @@ __global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevC
     }
 }
 
+// ------------------------------------------------------------ kappa_corot
+// get_angular_momentum_and_kappa_corot_weighted (kinematic_properties.py:266-425)
+// needs the direction of L before it can split the kinetic energy, so it runs
+// after k_moments has written L and vcom of every type: a second sweep adds up
+//   Kcorot = sum_{Li > 0, Ri2 != 0} 0.5 Li^2 / (m Ri2)   and   Mcounterrot = sum_{Li < 0} m
+// per selection (BoundSubhalo, apertures) and group (gas, stars, baryons) into the
+// kappa slots of the row; k_kappa_finish turns them into kappa_corot = Kcorot / K
+// and DtoT = 1 - 2 Mcounterrot / M (aperture_properties.py:1147-1270).
+struct KapSel {
+    double vc[3][3], lh[3][3];  // per group: reference velocity, unit angular momentum
+    int ok[3];
+    double R;
+    int incl, is_sub;
+    double* out;  // the block's 5 kappa slots
+};
+
+__device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl) {
+    const double* kin = blk + bl.kin;
+    const double Mg = blk[4], Ms = blk[6];
+    for (int g = 0; g < 3; g++) {
+        double L[3];
+        if (g < 2) {
+            const double* o = kin + 15 * (g == 0 ? 0 : 2);
+            for (int d = 0; d < 3; d++) { k.vc[g][d] = o[3 + d]; L[d] = o[6 + d]; }
+        } else {
+            for (int d = 0; d < 3; d++) {
+                L[d] = kin[45 + d];
+                k.vc[2][d] = (Mg + Ms) != 0.0 ? (Mg * kin[3 + d] + Ms * kin[30 + 3 + d]) / (Mg + Ms) : 0.0;
+            }
+        }
+        const double nrm = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+        k.ok[g] = nrm > 0.0;
+        for (int d = 0; d < 3; d++) k.lh[g][d] = nrm > 0.0 ? L[d] / nrm : 0.0;
+    }
+    k.out = blk + bl.kappa;
+}
+
+__global__ void __launch_bounds__(TB) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
+                                              const unsigned int* __restrict__ n_items_dev) {
+    __shared__ SweepShared SW;
+    __shared__ KapSel sel[1 + SOAP_MAX_APERTURES];
+    __shared__ double acc[1 + SOAP_MAX_APERTURES][5];
+    __shared__ int nsel;
+    const unsigned int n_items = *n_items_dev;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
+        const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+        if (c_hi <= c_lo || ha.status[h] >= 2) continue;
+        const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
+        const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
+        const double R = ha.rung_r[h];
+        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
+        const int32_t hidx = (int32_t)ha.index[h];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double* row = ha.out + (int64_t)h * ha.ncol;
+            int n = 0;
+            if (cfg.do_sub && c_lo == 0) {
+                kappa_refs(sel[n], row + cfg.lay.sub, cfg.lay.bsub);
+                sel[n].is_sub = 1; sel[n].incl = 0; sel[n].R = 0.0;
+                n++;
+            }
+            for (int a = 0; a < cfg.n_ap; a++)
+                if (off_ap + a >= c_lo && off_ap + a < c_hi) {
+                    kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap);
+                    sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a];
+                    n++;
+                }
+            nsel = n;
+        }
+        for (int i = threadIdx.x; i < (1 + SOAP_MAX_APERTURES) * 5; i += TB) (&acc[0][0])[i] = 0.0;
+        __syncthreads();
+        const int ns = nsel;
+        if (ns == 0) continue;
+        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+            if (!ok) return;
+            const uint32_t tc = (uint32_t)v.type[t];
+            if (tc != 0u && tc != 2u) return;  // gas and stars only
+            const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+            if (!(r2 <= r2max)) return;
+            const double x = rewrap_rel(v.px[t], cx, L, halfL);
+            const double y = rewrap_rel(v.py[t], cy, L, halfL);
+            const double z = rewrap_rel(v.pz[t], cz, L, halfL);
+            const double r = radius3(x, y, z);
+            const bool bound = v.grnr[t] == hidx;
+            const double m = (double)v.mass[t];
+            const double vx = (double)v.vx[t], vy = (double)v.vy[t], vz = (double)v.vz[t];
+            const double rr2 = x * x + y * y + z * z;
+            const int g0 = tc == 0u ? 0 : 1;
+            for (int s = 0; s < ns; s++) {
+                const KapSel& k = sel[s];
+                const bool in = k.is_sub ? bound : (r <= k.R && (k.incl || bound));
+                if (!in) continue;
+                for (int gi = 0; gi < 2; gi++) {
+                    const int g = gi == 0 ? g0 : 2;
+                    if (!k.ok[g]) continue;
+                    const double ux = vx - k.vc[g][0], uy = vy - k.vc[g][1], uz = vz - k.vc[g][2];
+                    const double lx = m * (y * uz - z * uy), ly = m * (z * ux - x * uz), lz = m * (x * uy - y * ux);
+                    const double Li = lx * k.lh[g][0] + ly * k.lh[g][1] + lz * k.lh[g][2];
+                    const double rdl = x * k.lh[g][0] + y * k.lh[g][1] + z * k.lh[g][2];
+                    const double Ri2 = rr2 - rdl * rdl;
+                    if (Ri2 != 0.0 && Li > 0.0) atomicAdd(&acc[s][g], 0.5 * (Li * Li / (m * Ri2)));
+                    if (g < 2 && Li < 0.0) atomicAdd(&acc[s][3 + g], m);
+                }
+            }
+        });
+        __syncthreads();
+        for (int i = threadIdx.x; i < ns * 5; i += TB) {
+            const double a = acc[i / 5][i % 5];
+            if (a != 0.0) atomicAdd(&sel[i / 5].out[i % 5], a);
+        }
+        __syncthreads();
+    }
+}
+
+// raw sums -> kappa_corot / DtoT, once per selection, at the rung that committed it
+__global__ void k_kappa_finish(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ list,
+                               const unsigned int* __restrict__ n_list) {
+    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_list) return;
+    const uint32_t h = list[it];
+    const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+    if (c_hi <= c_lo || ha.status[h] >= 2) return;
+    const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
+    double* row = ha.out + (int64_t)h * ha.ncol;
+    auto fin = [&](double* blk, const BlockLayout& bl) {
+        const double* kin = blk + bl.kin;
+        double* o = blk + bl.kappa;
+        const double Mg = blk[4], Ms = blk[6];
+        const double* gk = kin;        // gas: com 3, vcom 3, L 3, veldisp 6
+        const double* sk = kin + 30;   // stars
+        const double trg = gk[9] + gk[10] + gk[11], trs = sk[9] + sk[10] + sk[11];
+        const double Kg = 0.5 * Mg * trg, Ks = 0.5 * Ms * trs;
+        double Kb = 0.0;
+        if (Mg + Ms != 0.0) {
+            double dg = 0.0, ds = 0.0;
+            for (int d = 0; d < 3; d++) {
+                const double vb = (Mg * gk[3 + d] + Ms * sk[3 + d]) / (Mg + Ms);
+                dg += (gk[3 + d] - vb) * (gk[3 + d] - vb);
+                ds += (sk[3 + d] - vb) * (sk[3 + d] - vb);
+            }
+            Kb = 0.5 * (Mg * (trg + dg) + Ms * (trs + ds));
+        }
+        const double kc_g = o[0], kc_s = o[1], kc_b = o[2], mc_g = o[3], mc_s = o[4];
+        o[0] = Kg > 0.0 ? kc_g / Kg : 0.0;
+        o[1] = Ks > 0.0 ? kc_s / Ks : 0.0;
+        o[2] = Kb > 0.0 ? kc_b / Kb : 0.0;
+        o[3] = Mg != 0.0 ? 1.0 - 2.0 * mc_g / Mg : 0.0;
+        o[4] = Ms != 0.0 ? 1.0 - 2.0 * mc_s / Ms : 0.0;
+    };
+    if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
+    for (int a = 0; a < cfg.n_ap; a++)
+        if (off_ap + a >= c_lo && off_ap + a < c_hi) fin(row + cfg.lay.ap[a], cfg.lay.bap);
+}
+
 __global__ void k_write_input_cols(HaloArrays ha, int64_t nh) {
     int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
@@ -167,6 +323,20 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     else if (nty == 4) MOM(V_MIN, 4);
     else MOM(V_MIN, 1);
 #undef MOM
+    return 0;
+}
+
+int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
+                      const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* acc_list,
+                      const unsigned int* n_acc_dev, unsigned int n_acc_host, unsigned int grid,
+                      cudaStream_t stream) {
+    soap_handle* h = c->h;
+    if (!(cfg.flags & PF_KAPPA) || cfg.dmo) return 0;  // no gas or stars: every kappa slot stays zero
+    if (!(cfg.flags & PF_KIN)) SOAP_FAIL("soap_process_halos: kappa_corot needs the kinematics group (property_flags bit 0)");
+    unsigned int g = n_items_host < grid ? n_items_host : grid;
+    if (g < 1) g = 1;
+    LAUNCH(h, k_kappa, g, TB, 0, stream, c->v, ha, cfg, items, n_items_dev);
+    LAUNCH(h, k_kappa_finish, grid_for(n_acc_host, 128), 128, 0, stream, ha, cfg, acc_list, n_acc_dev);
     return 0;
 }
 

@@ -188,7 +188,14 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
                     Lscale = max(np.linalg.norm(Lr), 1e-3 * (o["Mgas"] + o["Mstar"]) * rscale * 300.0)
                     rep.check(pre + "Lbaryons", h, g("Lbaryons"), Lr, TOL_SECOND, scale=Lscale)
                 if kind == "sub" and "KineticEnergyTotal" in o:
-                    rep.check(pre + "Ekin_tot", h, g("Ekin_tot"), o["KineticEnergyTotal"], TOL_SECOND)
+                    # central second moment: can cancel to ~0 (a one-particle halo has none): scale with M v^2
+                    ek = float(o["KineticEnergyTotal"])
+                    rep.check(pre + "Ekin_tot", h, g("Ekin_tot"), ek, TOL_SECOND,
+                              scale=max(abs(ek), 1e-3 * o["Mtot"] * 300.0**2))
+            if flags & 2 and kind in ("sub", "ap"):
+                # kappa_corot / DtoT are ratios of second moments: absolute tolerance
+                for k in ("kappa_corot_gas", "kappa_corot_star", "kappa_corot_baryons", "DtoTgas", "DtoTstar"):
+                    rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_SECOND, scale=1.0)
             if flags & 4:
                 tn = "StellarInertiaTensor" if kind == "ap" else "TotalInertiaTensor"
                 for suffix in ("Noniterative", "ReducedNoniterative"):

@@ -56,6 +56,17 @@ def test_dummy_chunk_all_types_apertures():
     _run(data, H, cp, SO4[:3], aps, flags=1 | 4 | 8, dmo=False)
 
 
+def test_dummy_chunk_kappa_corot_and_disc_fractions():
+    """kappa_corot_{gas,star,baryons} and DtoT{gas,star} (kinematic_properties.py:266-425)
+    for BoundSubhalo and exclusive / inclusive apertures"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(3256, 30, boxsize=L, n_background=50000,
+                                npart_choices=(1, 10, 100, 1000, 5000))
+    aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 100.0) for incl in (0, 1)]
+    _run(data, H, cp, SO4[:1], aps, flags=1 | 2, dmo=False)
+
+
 def test_read_radius_too_small_status():
     """halos that cannot reach the target density inside read_radius come back
     with status 1 and the reference's updated radii (halo_tasks.py:166-181)"""
