@@ -28,6 +28,9 @@ int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, co
                       const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* acc_list,
                       const unsigned int* n_acc_dev, unsigned int n_acc_host, unsigned int grid,
                       cudaStream_t stream);
+int soap_launch_projected(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
+                          const unsigned int* n_items_dev, unsigned int n_items_host, unsigned int n_mslot,
+                          unsigned int grid, cudaStream_t stream);
 int soap_small_tier_fits(const DevCfg& cfg, int tier);
 int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int tier, const uint32_t* list,
                       const unsigned int* n_list, unsigned int n_list_upper, uint32_t* overflow,
@@ -532,7 +535,8 @@ DevCfg make_devcfg(const soap_halo_config& c) {
     const int pt[4] = {0, 1, 4, 5};
     for (int t = 0; t < 4; t++) d.soft[t] = c.softening[pt[t]];
     d.target_density = c.target_density;
-    d.do_sub = c.do_subhalo; d.n_so = c.n_so; d.n_ap = c.n_apertures; d.dmo = c.dmo;
+    d.do_sub = c.do_subhalo; d.n_so = c.n_so; d.n_ap = c.n_apertures; d.n_pj = c.n_projected; d.dmo = c.dmo;
+    for (int a = 0; a < SOAP_MAX_APERTURES; a++) d.pj_r[a] = c.proj_radius[a];
     for (int k = 0; k < SOAP_MAX_SO; k++) { d.so_rho[k] = c.so_reference_density[k]; d.so_virial[k] = c.so_virial[k]; }
     for (int a = 0; a < SOAP_MAX_APERTURES; a++) {
         d.ap_r[a] = c.ap_radius[a]; d.ap_mpc[a] = c.ap_physical_mpc[a]; d.ap_incl[a] = c.ap_inclusive[a];
@@ -546,7 +550,12 @@ int validate_cfg(const soap_halo_config* cfg) {
     if (cfg->n_so < 0 || cfg->n_so > SOAP_MAX_SO) SOAP_FAIL("config: n_so=%d outside [0,%d]", cfg->n_so, SOAP_MAX_SO);
     if (cfg->n_apertures < 0 || cfg->n_apertures > SOAP_MAX_APERTURES)
         SOAP_FAIL("config: n_apertures=%d outside [0,%d]", cfg->n_apertures, SOAP_MAX_APERTURES);
-    if (cfg->n_projected != 0) SOAP_FAIL("config: projected apertures are not implemented in this build");
+    if (cfg->n_projected < 0 || cfg->n_projected > SOAP_MAX_APERTURES)
+        SOAP_FAIL("config: n_projected=%d outside [0,%d]", cfg->n_projected, SOAP_MAX_APERTURES);
+    for (int a = 1; a < cfg->n_projected; a++)
+        if (cfg->proj_radius[a] < cfg->proj_radius[a - 1]) SOAP_FAIL("config: projected aperture radii must ascend");
+    if (cfg->n_projected > 0 && !cfg->do_subhalo)
+        SOAP_FAIL("config: projected apertures need BoundSubhalo first (they assume every bound particle is loaded)");
     if (!(cfg->boxsize > 0.0)) SOAP_FAIL("config: boxsize must be positive");
     for (int a = 1; a < cfg->n_apertures; a++)
         if (cfg->ap_radius[a] < cfg->ap_radius[a - 1]) SOAP_FAIL("config: aperture radii must ascend");
@@ -601,6 +610,17 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
     if (cfg->do_subhalo) block("BoundSubhalo/", 0);
     for (int k = 0; k < cfg->n_so; k++) block("SO/" + std::to_string(k) + "/", 1);
     for (int a = 0; a < cfg->n_apertures; a++) block("Aperture/" + std::to_string(a) + "/", 2);
+    for (int a = 0; a < cfg->n_projected; a++)
+        for (int ax = 0; ax < 3; ax++) {
+            const std::string p = "ProjectedAperture/" + std::to_string(a) + "/proj" + std::string(1, "xyz"[ax]) + "/";
+            const char* nm[] = {"Ngas", "Ndm", "Nstar", "Nbh", "Mgas", "Mdm", "Mstar", "Mbh"};
+            for (int i = 0; i < 8; i++) add(p + nm[i], 1);
+            add(p + "Mtot", 1); add(p + "com", 3); add(p + "vcom", 3);
+            add(p + "proj_veldisp_gas", 1); add(p + "proj_veldisp_dm", 1); add(p + "proj_veldisp_star", 1);
+            add(p + "HalfMassRadiusGas", 1); add(p + "HalfMassRadiusDm", 1); add(p + "HalfMassRadiusStar", 1);
+            add(p + "ProjectedTotalInertiaTensorNoniterative", 3);
+            add(p + "ProjectedTotalInertiaTensorReducedNoniterative", 3);
+        }
     if (buf && buflen > 0) {
         if ((int64_t)s.size() + 1 > buflen) { snprintf(g_soap_err, sizeof(g_soap_err), "soap_result_layout: buffer too small (%zu needed)", s.size() + 1); return -1; }
         memcpy(buf, s.data(), s.size());
@@ -691,7 +711,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     {
         long long prev = -1;
         for (int t = 0; t < NTIER; t++) {
-            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo);
+            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo) && dc.n_pj == 0;
             tl.lim[t] = tier_on[t] ? tier_nexp[t] : prev;  // a disabled tier takes no halos
             prev = tl.lim[t];
         }
@@ -856,6 +876,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             log.end(stream);
             log.begin("moments", stream);
             if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
+            if (soap_launch_projected(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
             if (soap_launch_kappa(c, dc, ha, items, &ctr->n_items, hc.n_items, acc_list, &ctr->n_acc, n_try, sweep_grid,
                                   stream))
                 return -1;

@@ -56,11 +56,17 @@ constexpr int N_INPUT_COLS = 6;  // status, n_loop, radius, n_pairs, search_radi
 constexpr int N_SUB_EXTRA = 5;   // HalfMassRadiusTot, EncloseRadius, Vmax_unsoft, R_vmax_unsoft, spin
 constexpr int N_SO_EXTRA = 9;    // r, SO_mass, spin, Mfrac_sat, Mfrac_ext, conc_unsoft, conc_soft, conc_dmo_unsoft, conc_dmo_soft
 
+// One projected aperture = three blocks (projx, projy, projz) of PJ_BLOCK columns:
+// N[4] M[4] Mtot com[3] vcom[3] proj_veldisp{gas,dm,star} HalfMassRadius{gas,dm,star}
+// ProjectedTotalInertiaTensorNoniterative[3] ...ReducedNoniterative[3]
+constexpr int PJ_BLOCK = 27;
+
 struct RowLayout {
     int ncol;
     int sub;                       // -1 if absent
     int so[SOAP_MAX_SO];
     int ap[SOAP_MAX_APERTURES];
+    int pj[SOAP_MAX_APERTURES];
     BlockLayout bsub, bso, bap;
 };
 
@@ -80,6 +86,10 @@ inline RowLayout row_layout(const soap_halo_config& cfg) {
         L.ap[a] = -1;
         if (a < cfg.n_apertures) { L.ap[a] = o; o += L.bap.size; }
     }
+    for (int a = 0; a < SOAP_MAX_APERTURES; a++) {
+        L.pj[a] = -1;
+        if (a < cfg.n_projected) { L.pj[a] = o; o += 3 * PJ_BLOCK; }
+    }
     L.ncol = o;
     return L;
 }
@@ -89,7 +99,8 @@ struct DevCfg {
     double L, halfL, G, H, kpc, r20, nu, mpc2c;
     double soft[4];  // by type code
     double target_density;
-    int do_sub, n_so, n_ap, dmo;
+    int do_sub, n_so, n_ap, n_pj, dmo;
+    double pj_r[SOAP_MAX_APERTURES];
     double so_rho[SOAP_MAX_SO];
     int so_virial[SOAP_MAX_SO];
     double ap_r[SOAP_MAX_APERTURES], ap_mpc[SOAP_MAX_APERTURES];

@@ -587,7 +587,8 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
             // halo_prop_list order: BoundSubhalo, SO..., apertures.  Properties
             // done at an earlier rung are not recomputed (halo_tasks.py:120-123),
             // and the done set is always a prefix of the list.
-            const int off_so = cfg.do_sub ? 1 : 0, off_ap = off_so + cfg.n_so, nprops = off_ap + n_ap;
+            const int off_so = cfg.do_sub ? 1 : 0, off_ap = off_so + cfg.n_so, off_pj = off_ap + n_ap;
+            const int nprops = off_pj + cfg.n_pj;
             const int p0 = ha.ndone[h];
             int p = p0;
             const double r_last = n > 0 ? __longlong_as_double((long long)R[n - 1].rbits) : 0.0;
@@ -662,10 +663,13 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                     S.so_r_[q] = sr->so_exists[q] ? SO_r : 0.0;
                 }
                     }
-                } else {
+                } else if (p < off_pj) {
                     // apertures ascending (aperture_properties.py:4140-4143)
                     const int a = p - off_ap;
                     if (ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+                } else {
+                    // projected apertures use bound particles only and never ask for a
+                    // larger radius (projected_aperture_properties.py:1888-1892)
                 }
                 if (!fail) p++;
             }

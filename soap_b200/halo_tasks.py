@@ -47,6 +47,8 @@ class HaloPropConfig:
     so: List[tuple] = field(default_factory=list)
     # each aperture: (radius in coordinate units, physical radius in Mpc, inclusive)
     apertures: List[tuple] = field(default_factory=list)
+    # each projected aperture: (radius in coordinate units, physical radius in Mpc)
+    projected: List[tuple] = field(default_factory=list)
     property_flags: int = 0
     dmo: bool = False
 
@@ -103,7 +105,14 @@ class HaloPropConfig:
             c.ap_radius[i] = float(r)
             c.ap_physical_mpc[i] = float(mpc)
             c.ap_inclusive[i] = int(bool(incl))
-        c.n_projected = 0
+        pj = sorted(self.projected, key=lambda a: a[0])
+        if len(pj) > _lib.SOAP_MAX_APERTURES:
+            raise ValueError("too many projected aperture variations")
+        self._sorted_projected = pj
+        c.n_projected = len(pj)
+        for i, (r, mpc) in enumerate(pj):
+            c.proj_radius[i] = float(r)
+            c.proj_physical_mpc[i] = float(mpc)
         c.property_flags = int(self.property_flags)
         c.dmo = int(self.dmo)
         return c

@@ -23,7 +23,7 @@ def oracle_params(cp, faithful=False):
     )
 
 
-def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True):
+def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True, projected=()):
     from soap_b200.halo_tasks import HaloPropConfig
 
     return HaloPropConfig(
@@ -31,11 +31,12 @@ def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True):
         mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
         H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
         nu_density=cp["nu_density"], phys_mpc_to_coord=cp["phys_mpc_to_coord"],
-        do_subhalo=do_subhalo, so=list(so), apertures=list(apertures), property_flags=flags, dmo=dmo,
+        do_subhalo=do_subhalo, so=list(so), apertures=list(apertures), projected=list(projected),
+        property_flags=flags, dmo=dmo,
     )
 
 
-def oracle_prop_list(params, cp, so, apertures, do_subhalo=True):
+def oracle_prop_list(params, cp, so, apertures, do_subhalo=True, projected=()):
     props = []
     if do_subhalo:
         props.append(oh.SubhaloOracle(params))
@@ -44,14 +45,16 @@ def oracle_prop_list(params, cp, so, apertures, do_subhalo=True):
     aps = sorted(apertures, key=lambda a: (a[0], a[2]))
     for i, (r, mpc, incl) in enumerate(aps):
         props.append(oh.ApertureOracle(params, r, mpc, bool(incl), f"{i}"))
+    for i, (r, mpc) in enumerate(sorted(projected, key=lambda a: a[0])):
+        props.append(oh.ProjectedApertureOracle(params, r, mpc, f"{i}"))
     return props
 
 
-def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True):
+def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True, projected=()):
     """Returns list (per halo) of (halo_result or None, info, input_halo)."""
     params = oracle_params(cp, faithful)
     meshes = {t: om.MeshOracle(d["Coordinates"], om.mesh_resolution(len(d["Masses"]))) for t, d in data.items()}
-    props = oracle_prop_list(params, cp, so, apertures, do_subhalo)
+    props = oracle_prop_list(params, cp, so, apertures, do_subhalo, projected)
     td = oh.target_density_of(props, params)
     out = []
     idxs = range(len(H["index"])) if halos is None else halos
@@ -82,6 +85,10 @@ def _group_names(props):
         elif isinstance(p, oh.ApertureOracle):
             names.append((f"Aperture/{a}/", p.group_name, "ap"))
             a += 1
+        elif isinstance(p, oh.ProjectedApertureOracle):
+            j = sum(1 for n in names if n[2] == "proj") // 3
+            for ax in "xyz":
+                names.append((f"ProjectedAperture/{j}/proj{ax}/", f"{p.group_name}/proj{ax}", "proj"))
     return names
 
 
@@ -138,6 +145,27 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
         for pre, gname, kind in names:
             o = ores.get(gname, {})
             g = lambda k: tab[pre + k][h]
+            if kind == "proj":
+                for k in ("Ngas", "Ndm", "Nstar", "Nbh"):
+                    rep.check(pre + k, h, g(k), o.get(k, 0), 0, exact=True)
+                for k in ("Mgas", "Mdm", "Mstar", "Mbh", "Mtot"):
+                    rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_MASS_RADIUS)
+                if "com" in o:
+                    d = (g("com") - np.asarray(o["com"]) + 0.5 * L) % L - 0.5 * L
+                    rep.check(pre + "com", h, d, np.zeros(3), TOL_MASS_RADIUS, scale=info["radius"])
+                    rep.check(pre + "vcom", h, g("vcom"), o["vcom"], TOL_FIRST_MOMENT, scale=300.0)
+                for nm in ("gas", "dm", "star"):
+                    # 1-D dispersion about the type's mean: cancels to 0 for a single particle
+                    rep.check(pre + f"proj_veldisp_{nm}", h, g(f"proj_veldisp_{nm}"), o.get(f"proj_veldisp_{nm}", 0.0),
+                              1e-2 * TOL_SECOND ** 0.5 if o.get(f"proj_veldisp_{nm}", 0.0) == 0.0 else TOL_SECOND, scale=300.0)
+                    if flags & 8:
+                        k = f"HalfMassRadius{nm.capitalize()}"
+                        rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_MASS_RADIUS)
+                for suffix in ("Noniterative", "ReducedNoniterative"):
+                    k = "ProjectedTotalInertiaTensor" + suffix
+                    ref = np.asarray(o.get(k, np.zeros(3)), dtype=np.float64)
+                    rep.check(pre + k, h, g(k), ref, TOL_SECOND, scale=(np.sqrt((ref[:2] ** 2).sum() + 2 * ref[2] ** 2) or None))
+                continue
             # counts: bit exact
             for k in ("Ngas", "Ndm", "Nstar", "Nbh"):
                 rep.check(pre + k, h, g(k), o.get(k, 0), 0, exact=True)

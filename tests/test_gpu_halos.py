@@ -11,13 +11,13 @@ pytestmark = pytest.mark.gpu
 SO4 = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
 
 
-def _run(data, H, cp, so, apertures, flags, dmo, fine_ppc=0, halos=None):
+def _run(data, H, cp, so, apertures, flags, dmo, fine_ppc=0, halos=None, projected=()):
     from soap_b200.halo_tasks import DeviceChunk, process_halos
 
-    cfg = cmp.device_config(cp, so=so, apertures=apertures, flags=flags, dmo=dmo)
+    cfg = cmp.device_config(cp, so=so, apertures=apertures, flags=flags, dmo=dmo, projected=projected)
     chunk = DeviceChunk(data, cp["boxsize"], fine_ppc=fine_ppc)
     res = process_halos(chunk, cfg, H)
-    oracle_out, props = cmp.run_oracle(data, H, cp, so, apertures, faithful=False, halos=halos)
+    oracle_out, props = cmp.run_oracle(data, H, cp, so, apertures, faithful=False, halos=halos, projected=projected)
     rep = cmp.compare(res, oracle_out, props, cp, halos=halos, flags=flags)
     print("max errors:", {k: float(f"{v:.3g}") for k, v in sorted(rep.maxerr.items())})
     print("timings:", chunk.timings())
@@ -65,6 +65,17 @@ def test_dummy_chunk_kappa_corot_and_disc_fractions():
                                 npart_choices=(1, 10, 100, 1000, 5000))
     aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 100.0) for incl in (0, 1)]
     _run(data, H, cp, SO4[:1], aps, flags=1 | 2, dmo=False)
+
+
+def test_dummy_chunk_projected_apertures():
+    """ProjectedAperture/{R}/proj{x,y,z}: masses, counts, com, vcom, 1-D velocity
+    dispersions and projected non-iterative inertia tensors, several radii at once"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(127, 30, boxsize=L, n_background=50000,
+                                npart_choices=(1, 10, 100, 1000, 5000))
+    pj = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3) for kpc in (10.0, 30.0, 50.0, 100.0)]
+    _run(data, H, cp, SO4[:1], [], flags=0, dmo=False, projected=pj)
 
 
 def test_read_radius_too_small_status():
