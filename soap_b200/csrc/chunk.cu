@@ -22,19 +22,121 @@ struct Geom {
     int res;
 };
 
-__global__ void __launch_bounds__(TB) k_fine_hist(const double* __restrict__ pos, int64_t n, Geom g,
-                                                  uint32_t* __restrict__ key,
-                                                  uint32_t* __restrict__ rank,
-                                                  uint32_t* __restrict__ count) {
+// ------------------------------------------------------------- radix sort
+// The cell-order permutation is an LSD radix sort of (cell id, particle index)
+// pairs, 8 bits per pass (3 passes for the 2^24 cells of a 256^3 mesh): per
+// pass a per-block digit histogram, one device-wide exclusive scan, and a
+// stable scatter (warp-level multi-split with match_any, no atomics).  Unlike
+// a counting sort with one returning atomic per particle on 16 M random
+// counters, every pass reads and writes its 8-byte pairs in tile-coherent runs.
+constexpr int RS_TB = 256, RS_IPT = 16, RS_TILE = RS_TB * RS_IPT, RS_NB = 256;
+
+__global__ void __launch_bounds__(TB) k_cell_keys(const double* __restrict__ pos, int64_t n, Geom g,
+                                                  uint32_t* __restrict__ key, uint32_t* __restrict__ val,
+                                                  uint32_t base) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int cx = cell_coord(pos[3 * i], g.pmin[0], g.cs[0], g.res);
     int cy = cell_coord(pos[3 * i + 1], g.pmin[1], g.cs[1], g.res);
     int cz = cell_coord(pos[3 * i + 2], g.pmin[2], g.cs[2], g.res);
-    uint32_t c = (uint32_t)cx + (uint32_t)g.res * ((uint32_t)cy + (uint32_t)g.res * (uint32_t)cz);
-    key[i] = c;
-    rank[i] = atomicAdd(&count[c], 1u);
+    key[i] = (uint32_t)cx + (uint32_t)g.res * ((uint32_t)cy + (uint32_t)g.res * (uint32_t)cz);
+    val[i] = base + (uint32_t)i;
 }
+
+__global__ void __launch_bounds__(RS_TB) k_rs_hist(const uint32_t* __restrict__ key, uint32_t n, int shift,
+                                                   uint32_t nblk, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t hist[RS_NB];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; k++) {
+        const uint32_t i = base + k * RS_TB + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(key[i] >> shift) & (RS_NB - 1)], 1u);
+    }
+    __syncthreads();
+    ghist[(size_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];  // digit-major: one scan gives global offsets
+}
+
+__global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __restrict__ key_in,
+                                                      const uint32_t* __restrict__ val_in, uint32_t n, int shift,
+                                                      uint32_t nblk, const uint32_t* __restrict__ goff,
+                                                      uint32_t* __restrict__ key_out,
+                                                      uint32_t* __restrict__ val_out) {
+    constexpr int NW = RS_TB / 32;
+    __shared__ uint32_t wcount[NW][RS_NB];  // running count of each digit within a warp's rows
+    __shared__ uint32_t wbase[NW][RS_NB];   // exclusive prefix over the warps + the block's global offset
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NW * RS_NB; i += RS_TB) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    // warp w owns the contiguous elements [w * 32 * IPT, (w + 1) * 32 * IPT) of the tile, row by row
+    const uint32_t wbeg = blockIdx.x * RS_TILE + wid * (32 * RS_IPT);
+    uint32_t k_[RS_IPT], v_[RS_IPT], rk[RS_IPT];
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        const uint32_t i = wbeg + r * 32 + lane;
+        const bool ok = i < n;
+        k_[r] = ok ? key_in[i] : 0xffffffffu;
+        v_[r] = ok ? val_in[i] : 0u;
+        const uint32_t d = ok ? ((k_[r] >> shift) & (RS_NB - 1)) : RS_NB;  // invalid lanes match each other only
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (ok && lane == leader) {
+            old = wcount[wid][d];
+            wcount[wid][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rk[r] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;  // RS_TB == RS_NB
+        uint32_t run = goff[(size_t)d * nblk + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            wbase[w][d] = run;
+            run += wcount[w][d];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; r++) {
+        const uint32_t i = wbeg + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (k_[r] >> shift) & (RS_NB - 1);
+            const uint32_t dst = wbase[wid][d] + rk[r];
+            key_out[dst] = k_[r];
+            val_out[dst] = v_[r];
+        }
+    }
+}
+
+// cell_off[c] = first sorted position whose key is >= c (cell_off[ncell] = n)
+__global__ void __launch_bounds__(TB) k_cell_offsets(const uint32_t* __restrict__ key, uint32_t n, uint32_t ncell,
+                                                     uint32_t* __restrict__ cell_off) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const long long prev = i == 0 ? -1ll : (long long)key[i - 1];
+    const long long cur = i == n ? (long long)ncell : (long long)key[i];
+    for (long long c = prev + 1; c <= cur; c++) cell_off[c] = i;
+}
+
+struct TypeIn {
+    const double* pos;
+    const float* mass;
+    const float* vel;
+    const void* grnr;
+    const void* fof;
+    uint32_t base, n;
+    int id64;
+    uint8_t tcode;
+};
+struct TypesIn {
+    TypeIn t[4];
+    int n;
+};
 
 struct SoAOut {
     double *px, *py, *pz;
@@ -44,35 +146,33 @@ struct SoAOut {
     uint32_t* orig;
 };
 
-template <bool ID64>
-__global__ void __launch_bounds__(TB) k_reorder(const double* __restrict__ pos,
-                                                const float* __restrict__ mass,
-                                                const float* __restrict__ vel,
-                                                const void* __restrict__ grnr,
-                                                const void* __restrict__ fof, int64_t n,
-                                                const uint32_t* __restrict__ key,
-                                                const uint32_t* __restrict__ rank,
-                                                const uint32_t* __restrict__ cell_off,
-                                                uint8_t tcode, SoAOut o) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t d = cell_off[key[i]] + rank[i];
-    o.px[d] = pos[3 * i];
-    o.py[d] = pos[3 * i + 1];
-    o.pz[d] = pos[3 * i + 2];
-    o.mass[d] = mass[i];
-    o.vx[d] = vel[3 * i];
-    o.vy[d] = vel[3 * i + 1];
-    o.vz[d] = vel[3 * i + 2];
-    if (ID64) {
-        o.grnr[d] = (int32_t)((const int64_t*)grnr)[i];
-        o.fof[d] = (int32_t)((const int64_t*)fof)[i];
+// cell-ordered SoA: slot d takes particle perm[d] (coalesced writes, gathered reads)
+__global__ void __launch_bounds__(TB) k_gather(TypesIn in, const uint32_t* __restrict__ perm, uint32_t n, SoAOut o) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const uint32_t src = perm[d];
+    int ti = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++)
+        if (k < in.n && src >= in.t[k].base) ti = k;
+    const TypeIn& T = in.t[ti];
+    const uint32_t i = src - T.base;
+    o.px[d] = T.pos[3 * (size_t)i];
+    o.py[d] = T.pos[3 * (size_t)i + 1];
+    o.pz[d] = T.pos[3 * (size_t)i + 2];
+    o.mass[d] = T.mass[i];
+    o.vx[d] = T.vel[3 * (size_t)i];
+    o.vy[d] = T.vel[3 * (size_t)i + 1];
+    o.vz[d] = T.vel[3 * (size_t)i + 2];
+    if (T.id64) {
+        o.grnr[d] = (int32_t)((const int64_t*)T.grnr)[i];
+        o.fof[d] = (int32_t)((const int64_t*)T.fof)[i];
     } else {
-        o.grnr[d] = ((const int32_t*)grnr)[i];
-        o.fof[d] = ((const int32_t*)fof)[i];
+        o.grnr[d] = ((const int32_t*)T.grnr)[i];
+        o.fof[d] = ((const int32_t*)T.fof)[i];
     }
-    o.type[d] = tcode;
-    o.orig[d] = (uint32_t)i;
+    o.type[d] = T.tcode;
+    o.orig[d] = i;
 }
 
 template <typename T>
@@ -148,42 +248,53 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     rc |= dev_alloc(c, &o.type, n); rc |= dev_alloc(c, &o.orig, n);
     if (rc) { soap_chunk_destroy(c); return -1; }
     uint32_t* key = (uint32_t*)h->get("chunk_key", sizeof(uint32_t) * (size_t)n);
-    uint32_t* rank = (uint32_t*)h->get("chunk_rank", sizeof(uint32_t) * (size_t)n);
-    if (!key || !rank) { soap_chunk_destroy(c); return -1; }
+    uint32_t* val = (uint32_t*)h->get("chunk_val", sizeof(uint32_t) * (size_t)n);
+    uint32_t* key2 = (uint32_t*)h->get("chunk_key2", sizeof(uint32_t) * (size_t)n);
+    uint32_t* val2 = (uint32_t*)h->get("chunk_val2", sizeof(uint32_t) * (size_t)n);
+    const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t* ghist = (uint32_t*)h->get("chunk_ghist", sizeof(uint32_t) * (size_t)RS_NB * nblk);
+    if (!key || !val || !key2 || !val2 || !ghist) { soap_chunk_destroy(c); return -1; }
     Geom g;
     for (int d = 0; d < 3; d++) { g.pmin[d] = v.pmin[d]; g.cs[d] = v.cs[d]; }
     g.res = res;
 #define CK(stmt) do { if ((stmt) != 0) { soap_chunk_destroy(c); return -1; } } while (0)
 #define CKL(...) do { auto _f = [&]() -> int { __VA_ARGS__; return 0; }; if (_f() != 0) { soap_chunk_destroy(c); return -1; } } while (0)
-    c->create_log.begin("mesh_hist", stream);
-    CKL(CUDA_TRY(cudaMemsetAsync(cell_off, 0, sizeof(uint32_t) * (ncell + 1), stream)));
+    c->create_log.begin("mesh_keys", stream);
+    TypesIn tin;
+    tin.n = 0;
     int64_t base = 0;
     for (int t = 0; t < n_types; t++) {
         if (types[t].n == 0) continue;
-        CKL(LAUNCH(h, k_fine_hist, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos, types[t].n, g,
-                   key + base, rank + base, cell_off));
-        base += types[t].n;
-    }
-    c->create_log.end(stream);
-    c->create_log.begin("mesh_scan", stream);
-    CK(soap_exclusive_scan_u32(h, cell_off, cell_off, nullptr, ncell + 1, nullptr, stream));
-    c->create_log.end(stream);
-    c->create_log.begin("reorder", stream);
-    base = 0;
-    for (int t = 0; t < n_types; t++) {
-        if (types[t].n == 0) continue;
+        CKL(LAUNCH(h, k_cell_keys, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos, types[t].n, g, key + base,
+                   val + base, (uint32_t)base));
         uint8_t tc = (uint8_t)ptype_code(types[t].ptype);
         c->type_present[tc] = 1;
-        if (types[t].ids_are_int64)
-            CKL(LAUNCH(h, k_reorder<true>, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos,
-                       types[t].mass, types[t].vel, types[t].grnr, types[t].fof, types[t].n, key + base,
-                       rank + base, cell_off, tc, o));
-        else
-            CKL(LAUNCH(h, k_reorder<false>, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos,
-                       types[t].mass, types[t].vel, types[t].grnr, types[t].fof, types[t].n, key + base,
-                       rank + base, cell_off, tc, o));
+        TypeIn& T = tin.t[tin.n++];
+        T.pos = types[t].pos; T.mass = types[t].mass; T.vel = types[t].vel;
+        T.grnr = types[t].grnr; T.fof = types[t].fof;
+        T.base = (uint32_t)base; T.n = (uint32_t)types[t].n; T.id64 = types[t].ids_are_int64; T.tcode = tc;
         base += types[t].n;
     }
+    c->create_log.end(stream);
+    c->create_log.begin("mesh_sort", stream);
+    {
+        int bits = 0;
+        while ((1ll << bits) < ncell) bits++;
+        uint32_t *ki = key, *vi = val, *ko = key2, *vo = val2;
+        for (int shift = 0; shift < bits; shift += 8) {
+            CKL(LAUNCH(h, k_rs_hist, nblk, RS_TB, 0, stream, ki, (uint32_t)n, shift, nblk, ghist));
+            CK(soap_exclusive_scan_u32(h, ghist, ghist, nullptr, (int64_t)RS_NB * nblk, nullptr, stream));
+            CKL(LAUNCH(h, k_rs_scatter, nblk, RS_TB, 0, stream, ki, vi, (uint32_t)n, shift, nblk, ghist, ko, vo));
+            uint32_t* t1 = ki; ki = ko; ko = t1;
+            uint32_t* t2 = vi; vi = vo; vo = t2;
+        }
+        key = ki;
+        val = vi;
+    }
+    CKL(LAUNCH(h, k_cell_offsets, grid_for(n + 1, TB), TB, 0, stream, key, (uint32_t)n, (uint32_t)ncell, cell_off));
+    c->create_log.end(stream);
+    c->create_log.begin("reorder", stream);
+    CKL(LAUNCH(h, k_gather, grid_for(n, TB), TB, 0, stream, tin, val, (uint32_t)n, o));
     c->create_log.end(stream);
 #undef CK
 #undef CKL
