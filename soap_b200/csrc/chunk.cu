@@ -327,7 +327,7 @@ int64_t soap_chunk_last_pairs(const soap_chunk* c) { return c ? c->last_pairs : 
 int64_t soap_chunk_timings(const soap_chunk* c, char* buf, int64_t buflen) {
     if (!c || !buf || buflen <= 0) return 0;
     std::string s;
-    char line[160];
+    char line[512];
     for (auto& kv : c->create_log.ms) {
         snprintf(line, sizeof(line), "create/%s:%.6f\n", kv.first.c_str(), kv.second);
         s += line;

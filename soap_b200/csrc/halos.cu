@@ -41,11 +41,11 @@ namespace {
 constexpr int TB = SWEEP_NT;
 constexpr int SB_CAP = 4096;     // records of one bucket sorted in shared memory (64 KB)
 constexpr int SMALL_CAP = 512;   // small-bucket class (8 KB)
-constexpr int FINE_TARGET = 8;   // expected records per fine radial bin (sorted by one warp in registers)
+constexpr int FINE_TARGET = 12;  // expected records per fine radial bin (sorted by one warp in registers)
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
 // halos with up to this many bound particles start in fused tier 0 / 1 / 2; larger ones take the general path
-constexpr long long SMALL_NEXP_0 = 40, SMALL_NEXP_1 = 200, SMALL_NEXP_2 = 800;
+constexpr long long SMALL_NEXP_0 = 90, SMALL_NEXP_1 = 200, SMALL_NEXP_2 = 800;
 
 struct Bucket {
     unsigned long long start;

@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(512, 1) k_small_warps(ChunkView v, HaloArrays 
     int32_t hidx = 0;
     bool central = false;
     int n_so = 0, nloop = 0, nrows = 0;
+    bool look1 = false;  // the look-ahead sphere did not fit: sweep the current rung alone
 
     while (true) {
         // ============ phase 1: fetch halos and walk their ladder until one needs a solve
@@ -386,13 +387,17 @@ __global__ void __launch_bounds__(512, 1) k_small_warps(ChunkView v, HaloArrays 
                 nloop = ha.nloop[h];
                 state = WS_RUNG;
             }
-            // ---- rows of this rung
+            // ---- rows of the furthest of the next rungs (ladder look-ahead: one sweep bins the
+            // sphere by rung, like k_count; a sphere too large for this tier is retried rung by rung)
+            constexpr int LOOK = 4;
+            double rr[LOOK];
+            int nr = ladder_radii(cur, ha.rr_in[h], look1 ? 1 : LOOK, rr);
+            const double rsweep = rr[nr - 1];
             __syncwarp();
-            if (lane < 3) halo_ranges(v, cx, cy, cz, cur, W.rg, lane);
+            if (lane < 3) halo_ranges(v, cx, cy, cz, rsweep, W.rg, lane);
             __syncwarp();
             const RowIter ri = row_iter(W.rg);
             nrows = ri.nrows;
-            r2max = __dmul_rn(cur, cur);
             bool too_big = nrows > 32;
             if (!too_big) {
                 uint32_t s0 = 0, s1 = 0;
@@ -413,43 +418,79 @@ __global__ void __launch_bounds__(512, 1) k_small_warps(ChunkView v, HaloArrays 
             }
             int action;
             if (too_big) {
+                if (nr > 1) { look1 = true; continue; }  // try again with this rung alone
                 action = ACT_OVERFLOW;
             } else {
-                nloop++;  // halo_tasks.py:75
-                // ---- count + enclosed mass (halo_tasks.py:84-97)
-                uint32_t cnt = 0;
-                double msum = 0.0;
+                // ---- count + enclosed mass per rung (halo_tasks.py:84-97)
+                double r2k[LOOK];
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) r2k[k] = k < nr ? __dmul_rn(rr[k], rr[k]) : -1.0;
+                uint32_t cnt[LOOK];
+                double msum[LOOK];
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) { cnt[k] = 0; msum[k] = 0.0; }
                 for (uint32_t j = lane; j < total; j += 32) {
                     const uint32_t t = cand_slot(j, nrows);
                     const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
-                    if (r2 <= r2max) { cnt++; msum += (double)v.mass[t]; }
+                    if (r2 <= r2k[nr - 1]) {
+                        const double m = (double)v.mass[t];
+                        bool placed = false;
+#pragma unroll
+                        for (int k = 0; k < LOOK; k++)
+                            if (!placed && k < nr && r2 <= r2k[k]) { cnt[k]++; msum[k] += m; placed = true; }
+                    }
                 }
-                cnt = (uint32_t)warp_sum_u64(cnt);
-                msum = warp_sum(msum);
-                // ---- density gate and ladder step (halo_tasks.py:97-103,166-187)
-                action = ACT_TRY;
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) {
+                    cnt[k] = (uint32_t)warp_sum_u64(cnt[k]);
+                    msum[k] = warp_sum(msum[k]);
+                }
+                // ---- density gate and ladder steps (halo_tasks.py:73-103,166-187)
+                action = ACT_RETRY;
+                uint32_t ccum = 0;
+                int kacc = 0;
                 if (lane == 0) {
-                    const double density = msum / (4.0 / 3.0 * SOAP_PI * (cur * cur * cur));
                     const bool has_target = central && cfg.target_density > 0.0;  // halo_tasks.py:381
-                    if (has_target && !(density <= cfg.target_density)) {
-                        action = ladder_step(ha, h, 0.0) ? ACT_RETRY : ACT_DONE;
-                    } else if (cnt > (uint32_t)CAP) {
-                        action = ACT_OVERFLOW;
-                    } else {
-                        // what k_plan_items / k_gate leave behind for the scan and moment stages
-                        ha.cnt[h] = cnt;
-                        ha.msum[h] = msum;
-                        ha.rung_r[h] = cur;
-                        ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
-                        ha.state[h] = ST_TRY;
+                    double mcum = 0.0;
+                    bool pending = true;
+                    for (int k = 0; k < nr && pending; k++) {
+                        nloop++;  // halo_tasks.py:75
+                        const double r = ha.cur_r[h];
+                        ccum += cnt[k];
+                        mcum += msum[k];
+                        const double density = mcum / (4.0 / 3.0 * SOAP_PI * (r * r * r));
+                        if (!has_target || density <= cfg.target_density) {
+                            kacc = k;
+                            if (ccum > (uint32_t)CAP) {
+                                action = ACT_OVERFLOW;
+                                nloop--;  // the next tier repeats this rung
+                            } else {
+                                action = ACT_TRY;
+                                // what k_plan_items / k_gate leave behind for the scan and moment stages
+                                ha.cnt[h] = ccum;
+                                ha.msum[h] = mcum;
+                                ha.rung_r[h] = r;
+                                ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+                                ha.state[h] = ST_TRY;
+                            }
+                            break;
+                        }
+                        pending = ladder_step(ha, h, 0.0);
+                        if (!pending) action = ACT_DONE;
                     }
                     atomicAdd(&ctr->candidates, (unsigned long long)total);
-                    atomicAdd(&ctr->count_pairs, (unsigned long long)cnt);
+                    atomicAdd(&ctr->count_pairs, (unsigned long long)ccum);
                 }
                 action = __shfl_sync(0xffffffffu, action, 0);
-                if (action == ACT_OVERFLOW) nloop--;  // the next tier repeats this rung
-                n = cnt;
+                nloop = __shfl_sync(0xffffffffu, nloop, 0);
+                n = __shfl_sync(0xffffffffu, ccum, 0);
+                kacc = __shfl_sync(0xffffffffu, kacc, 0);
+                if (action == ACT_TRY) {
+                    cur = rr[kacc];
+                    r2max = r2k[kacc];
+                }
             }
+            look1 = false;
             if (action == ACT_RETRY) {
                 cur = __shfl_sync(0xffffffffu, lane == 0 ? ha.cur_r[h] : 0.0, 0);
             } else if (action == ACT_TRY) {
@@ -658,7 +699,7 @@ int launch_tier(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const ui
 
 }  // namespace
 
-// Tiers 0 and 1: spheres of up to 128 / 512 particles, one warp per halo, the
+// Tiers 0 and 1: spheres of up to 256 / 512 particles, one warp per halo, the
 // warps of a CTA in lock step (k_small_warps); tier 2: up to 2048, one CTA of
 // 256 threads per halo (k_small_halos).  A tier is used only if it fits.
 int soap_small_tier_fits(const DevCfg& cfg, int tier) {
@@ -670,7 +711,7 @@ int soap_small_tier_fits(const DevCfg& cfg, int tier) {
         const size_t smem = full ? tier_smem<V_FULL, 256, 2048>(stride) : tier_smem<V_MIN, 256, 2048>(stride);
         return smem <= SMALL_SMEM_MAX ? 1 : 0;
     }
-#define SLOT(NCH, VV) (tier == 0 ? sizeof(WarpSlot<NCH, VV, 128>) : sizeof(WarpSlot<NCH, VV, 512>))
+#define SLOT(NCH, VV) (tier == 0 ? sizeof(WarpSlot<NCH, VV, 256>) : sizeof(WarpSlot<NCH, VV, 512>))
     if (cfg.dmo) slot = full ? SLOT(2, V_FULL) : SLOT(2, V_MIN);
     else slot = full ? SLOT(8, V_FULL) : SLOT(8, V_MIN);
 #undef SLOT
@@ -686,7 +727,7 @@ int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, in
     const unsigned int cap = n_list_upper < 1 ? 1 : n_list_upper;
 #define ARGS c, cfg, ha, list, n_list, overflow, n_overflow, queue_cursor, ctr, stride, cap, stream
 #define GO(NCH, VV)                                                  \
-    (tier == 0   ? launch_warp_tier<NCH, VV, 128>(ARGS)              \
+    (tier == 0   ? launch_warp_tier<NCH, VV, 256>(ARGS)              \
      : tier == 1 ? launch_warp_tier<NCH, VV, 512>(ARGS)              \
                  : launch_tier<NCH, VV, 256, 2048>(ARGS))
     if (cfg.dmo) return full ? GO(2, V_FULL) : GO(2, V_MIN);
