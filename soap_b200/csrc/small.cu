@@ -26,7 +26,7 @@ struct SmallCtl {
     uint32_t total;    // candidates of the current rung
     unsigned int n_in, n_stage;
     double msum;
-    int action;
+    int action, kacc;
     unsigned long long minr;
     int32_t minfof;
 };
@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(NT, (V <= 16 ? 512 : 256) / NT > 16 ? 16 : (V 
     __shared__ unsigned long long w_u64[NW];
     __shared__ int32_t w_i32[NW];
     __shared__ SmallCtl B;
+    __shared__ uint32_t w_cnt[NW][4];
+    __shared__ double w_msum[NW][4];
+    __shared__ int nloop_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double L = v.L, halfL = 0.5 * v.L;
 
@@ -107,15 +110,20 @@ __global__ void __launch_bounds__(NT, (V <= 16 ? 512 : 256) / NT > 16 ? 16 : (V 
         const bool central = ha.central[h] == 1;
         const int n_so = central ? cfg.n_so : 0;
         double cur = ha.cur_r[h];
-        int nloop = ha.nloop[h];
+        if (threadIdx.x == 0) nloop_s = ha.nloop[h];
+        bool look1 = false;  // the look-ahead sphere did not fit: sweep the current rung alone
         int action = ACT_DONE;
         while (true) {
-            // ------------------------------------------------ rows of this rung
+            // ------------------------ rows of the furthest of the next rungs (ladder look-ahead:
+            // one sweep bins the sphere by rung, like k_count; if that sphere does not fit this
+            // tier the current rung is swept alone)
+            constexpr int LOOK = 4;
+            double rr[LOOK];
+            const int nr = ladder_radii(cur, ha.rr_in[h], look1 ? 1 : LOOK, rr);
             __syncthreads();
-            if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, cur, rg, threadIdx.x);
+            if (threadIdx.x < 3) halo_ranges(v, cx, cy, cz, rr[nr - 1], rg, threadIdx.x);
             __syncthreads();
             const RowIter ri = row_iter(rg);
-            const double r2max = __dmul_rn(cur, cur);
             bool too_big = ri.nrows > NT;
             uint32_t total = 0;
             if (!too_big) {
@@ -142,54 +150,81 @@ __global__ void __launch_bounds__(NT, (V <= 16 ? 512 : 256) / NT > 16 ? 16 : (V 
                 too_big = total > CAND_MAX;
                 __syncthreads();
             }
-            if (too_big) { action = ACT_OVERFLOW; break; }
-            nloop++;  // halo_tasks.py:75
-            // ------------------------------------ count + enclosed mass (halo_tasks.py:84-97)
+            if (too_big) {
+                if (nr > 1) { look1 = true; continue; }
+                action = ACT_OVERFLOW;
+                break;
+            }
+            look1 = false;
+            // ------------------------------------ count + enclosed mass per rung (halo_tasks.py:84-97)
+            double r2k[LOOK];
+#pragma unroll
+            for (int k = 0; k < LOOK; k++) r2k[k] = k < nr ? __dmul_rn(rr[k], rr[k]) : -1.0;
             {
-                uint32_t cnt = 0;
-                double msum = 0.0;
+                uint32_t cnt[LOOK];
+                double msum[LOOK];
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) { cnt[k] = 0; msum[k] = 0.0; }
                 for (uint32_t j = threadIdx.x; j < total; j += NT) {
                     const uint32_t t = cand_slot(j, ri.nrows);
                     const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
-                    if (r2 <= r2max) { cnt++; msum += (double)v.mass[t]; }
+                    if (r2 <= r2k[nr - 1]) {
+                        const double m = (double)v.mass[t];
+                        bool placed = false;
+#pragma unroll
+                        for (int k = 0; k < LOOK; k++)
+                            if (!placed && k < nr && r2 <= r2k[k]) { cnt[k]++; msum[k] += m; placed = true; }
+                    }
                 }
-                cnt = (uint32_t)warp_sum_u64(cnt);
-                msum = warp_sum(msum);
-                if (lane == 0) { w_u32[wid] = cnt; w_f64[wid] = msum; }
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) {
+                    const uint32_t c = (uint32_t)warp_sum_u64(cnt[k]);
+                    const double m = warp_sum(msum[k]);
+                    if (lane == 0) { w_cnt[wid][k] = c; w_msum[wid][k] = m; }
+                }
                 __syncthreads();
                 if (threadIdx.x == 0) {
-                    uint32_t c = 0;
-                    double m = 0.0;
-                    for (int w = 0; w < NW; w++) { c += w_u32[w]; m += w_f64[w]; }
-                    // density gate and ladder step (halo_tasks.py:97-103,166-187)
-                    const double density = m / (4.0 / 3.0 * SOAP_PI * (cur * cur * cur));
+                    // density gate and ladder steps (halo_tasks.py:73-103,166-187)
                     const bool has_target = central && cfg.target_density > 0.0;  // halo_tasks.py:381
-                    int act;
-                    if (has_target && !(density <= cfg.target_density)) {
-                        act = ladder_step(ha, h, 0.0) ? ACT_RETRY : ACT_DONE;
-                    } else if (c > (uint32_t)CAP) {
-                        act = ACT_OVERFLOW;
-                    } else {
-                        act = ACT_TRY;
-                        // what k_plan_items / k_gate leave behind for the scan and moment stages
-                        ha.cnt[h] = c;
-                        ha.msum[h] = m;
-                        ha.rung_r[h] = cur;
-                        ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
-                        ha.state[h] = ST_TRY;
+                    uint32_t ccum = 0;
+                    double mcum = 0.0;
+                    int act = ACT_RETRY, kacc = 0;
+                    bool pending = true;
+                    for (int k = 0; k < nr && pending; k++) {
+                        nloop_s++;  // halo_tasks.py:75
+                        const double r = ha.cur_r[h];
+                        for (int w = 0; w < NW; w++) { ccum += w_cnt[w][k]; mcum += w_msum[w][k]; }
+                        const double density = mcum / (4.0 / 3.0 * SOAP_PI * (r * r * r));
+                        if (!has_target || density <= cfg.target_density) {
+                            kacc = k;
+                            if (ccum > (uint32_t)CAP) {
+                                act = ACT_OVERFLOW;
+                                nloop_s--;  // the next tier repeats this rung
+                            } else {
+                                act = ACT_TRY;
+                                // what k_plan_items / k_gate leave behind for the scan and moment stages
+                                ha.cnt[h] = ccum;
+                                ha.msum[h] = mcum;
+                                ha.rung_r[h] = r;
+                                ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+                                ha.state[h] = ST_TRY;
+                            }
+                            break;
+                        }
+                        pending = ladder_step(ha, h, 0.0);
+                        if (!pending) act = ACT_DONE;
                     }
-                    B.n_in = c; B.msum = m; B.action = act; B.n_stage = 0;
+                    B.n_in = ccum; B.msum = mcum; B.action = act; B.n_stage = 0; B.kacc = kacc;
                     atomicAdd(&ctr->candidates, (unsigned long long)total);
-                    atomicAdd(&ctr->count_pairs, (unsigned long long)c);
+                    atomicAdd(&ctr->count_pairs, (unsigned long long)ccum);
                 }
                 __syncthreads();
             }
             action = B.action;
             if (action == ACT_RETRY) { cur = ha.cur_r[h]; continue; }
-            if (action != ACT_TRY) {
-                if (action == ACT_OVERFLOW) nloop--;  // the next tier repeats this rung
-                break;
-            }
+            if (action != ACT_TRY) break;
+            cur = rr[B.kacc];
+            const double r2max = r2k[B.kacc];
             const uint32_t n = B.n_in;
             // ------------------------------------- gather + re-wrap (halo_tasks.py:106-117)
             {
@@ -301,7 +336,7 @@ __global__ void __launch_bounds__(NT, (V <= 16 ? 512 : 256) / NT > 16 ? 16 : (V 
             break;
         }
         if (threadIdx.x == 0) {
-            ha.nloop[h] = nloop;
+            ha.nloop[h] = nloop_s;
             if (action == ACT_OVERFLOW) {
                 ha.state[h] = ST_PENDING;
                 overflow[atomicAdd(n_overflow, 1u)] = h;
