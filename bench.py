@@ -54,7 +54,8 @@ ALG_BYTES = {
     "sort": 32,      # per record: 16 B in + 16 B out
     "scan_solve": 16,  # per record (one read of the sorted profile)
     "moments": 48,   # per pair: position 24, mass 4, velocity 12, grnr 4, fof 4
-    "small_halos": 48,  # fused tiers (small.cu), per pair: the whole stage B+C figure of SURVEY.md 8(d)
+    # fused tiers (small.cu), per pair: the whole stage B+C figure of SURVEY.md 8(d)
+    "small_0": 48, "small_1": 48, "small_2": 48,
 }
 
 
@@ -441,7 +442,9 @@ def main():
         "sort": (stats.get("try_pairs", 0.0), ph.get("halos/sort", 0.0)),
         "scan_solve": (stats.get("try_pairs", 0.0), ph.get("halos/scan_solve", 0.0)),
         "moments": (stats.get("moment_pairs", 0.0), ph.get("halos/moments", 0.0)),
-        "small_halos": (stats.get("small_pairs", 0.0), sum(ph.get(f"halos/small_{t}", 0.0) for t in range(3))),
+        "small_0": (stats.get("small_pairs_0", 0.0), ph.get("halos/small_0", 0.0)),
+        "small_1": (stats.get("small_pairs_1", 0.0), ph.get("halos/small_1", 0.0)),
+        "small_2": (stats.get("small_pairs_2", 0.0), ph.get("halos/small_2", 0.0)),
     }
     kernels = {}
     for k, (n_units, t_ms) in units.items():
@@ -449,8 +452,15 @@ def main():
         kernels[k] = {"ms": round(t_ms, 4), "units": int(n_units), "alg_bytes_per_unit": ALG_BYTES[k],
                       "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 4)}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")))
+        traffic = tr.get(args.workload, {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None}
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic,
+                "launches_per_step": 1 if dom.startswith("small") or dom == "mesh" else int(stats.get("rounds", 1))}
     total_alg = 32.0 * n_part + 48.0 * pairs + 8.0 * H * ncol
     kern_ms = sum(v["ms"] for v in kernels.values())
 

@@ -338,10 +338,11 @@ int64_t soap_chunk_timings(const soap_chunk* c, char* buf, int64_t buflen) {
     }
     snprintf(line, sizeof(line),
              "stat/pairs:%lld\nstat/candidates:%lld\nstat/count_pairs:%lld\nstat/try_pairs:%lld\n"
-             "stat/moment_pairs:%lld\nstat/rounds:%d\nstat/res:%d\nstat/small_pairs:%lld\n",
+             "stat/moment_pairs:%lld\nstat/rounds:%d\nstat/res:%d\nstat/small_pairs:%lld\nstat/small_pairs_0:%lld\nstat/small_pairs_1:%lld\nstat/small_pairs_2:%lld\n",
              (long long)c->last_pairs, (long long)c->last_candidates, (long long)c->last_count_pairs,
              (long long)c->last_try_pairs, (long long)c->last_mom_pairs, c->last_rounds, c->v.res,
-             (long long)c->last_small_pairs);
+             (long long)c->last_small_pairs, (long long)c->last_tier_pairs[0], (long long)c->last_tier_pairs[1],
+             (long long)c->last_tier_pairs[2]);
     s += line;
     int64_t m = (int64_t)s.size() < buflen - 1 ? (int64_t)s.size() : buflen - 1;
     memcpy(buf, s.data(), m);

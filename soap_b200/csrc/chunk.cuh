@@ -44,6 +44,7 @@ struct PhaseLog {
         for (auto& sp : spans) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) ms[sp.name] += t;
+            else cudaGetLastError();  // an unfinished span must not poison the next launch check
             pool.push_back(sp.e0);
             pool.push_back(sp.e1);
         }
@@ -63,6 +64,7 @@ struct soap_chunk {
     uint32_t* orig = nullptr;  // [n] index within the particle's own ptype array
     int64_t last_pairs = 0;
     int64_t last_small_pairs = 0;  // of which handled by the fused small-halo tiers
+    int64_t last_tier_pairs[3] = {0, 0, 0};
     int64_t last_candidates = 0;
     int64_t last_count_pairs = 0, last_try_pairs = 0, last_mom_pairs = 0;
     int last_rounds = 0;

@@ -314,11 +314,11 @@ __global__ void __launch_bounds__(TB) k_fine_hist_halo(ChunkView v, HaloArrays h
 // rare larger bins become buckets of the CTA-wide sort kernels.
 constexpr int BIN_SMEM = 256;
 __global__ void __launch_bounds__(256) k_sort_bins(const int64_t* __restrict__ fine_excl, uint32_t n_fine,
-                                                   Counters* ctr, Rec* __restrict__ recs,
+                                                   Counters* ctr, int use_single_base, Rec* __restrict__ recs,
                                                    Bucket* __restrict__ bkt_big, Bucket* __restrict__ bkt_huge) {
     __shared__ Rec sm[8][BIN_SMEM];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned long long base = ctr->rec_single;  // multi region follows the single region
+    const unsigned long long base = use_single_base ? ctr->rec_single : 0ull;  // multi region follows the single region
     const uint32_t nwarp = gridDim.x * 8;
     for (uint32_t b = blockIdx.x * 8 + wid; b < n_fine; b += nwarp) {
         const unsigned long long e0 = (unsigned long long)fine_excl[b];
@@ -475,6 +475,191 @@ __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevC
                 if (s_minr[w] < minr || (s_minr[w] == minr && s_minfof[w] < minfof)) { minr = s_minr[w]; minfof = s_minfof[w]; }
             item_minr[it] = minr;
             item_minfof[it] = minfof;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------- projected half-mass radii
+// get_half_weight_radius on the projected radius (projected_aperture_properties.py:
+// 953-986 with half_mass_radius.py:16-97), per projection axis: the halo's bound
+// particles are binned by projected radius, every bin is sorted (k_sort_bins), and
+// a streaming per-type cumulative sum finds, for every aperture and type, the record
+// at which the mass inside the aperture is half enclosed.
+struct PjPlan {
+    uint32_t* nfine;       // [H] bins of the halo (0 = not planned this rung)
+    uint32_t* fine_off;    // [H] first bin
+    unsigned int* n_fine;  // device total
+};
+
+__global__ void k_pj_plan(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ acc_list,
+                          const unsigned int* __restrict__ n_acc, PjPlan pl) {
+    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_acc) return;
+    const uint32_t h = acc_list[it];
+    const int off_pj = (cfg.do_sub ? 1 : 0) + cfg.n_so + cfg.n_ap;
+    const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+    pl.nfine[h] = 0;
+    if (c_hi <= c_lo || ha.status[h] >= 2 || c_hi <= off_pj || c_lo > off_pj) return;
+    const ScanRes* sr = ha.sres + h;
+    const uint32_t nb = sr->bound_count[0] + sr->bound_count[1] + sr->bound_count[2] + sr->bound_count[3];
+    uint32_t nf = nb / FINE_TARGET;
+    if (nf < 16) nf = 16;
+    pl.nfine[h] = nf;
+    pl.fine_off[h] = atomicAdd(pl.n_fine, nf);
+}
+
+// FILL = false: histogram of the bound particles over the halo's bins of projected
+// radius; FILL = true: scatter their records (projected radius, mass, type) into the bins
+template <bool FILL>
+__global__ void __launch_bounds__(TB) k_pj_bins(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
+                                                const unsigned int* __restrict__ n_items_dev, PjPlan pl, int ax,
+                                                uint32_t* __restrict__ fine_cnt,
+                                                const int64_t* __restrict__ fine_excl, Rec* __restrict__ recs) {
+    __shared__ SweepShared S;
+    const unsigned int n_items = *n_items_dev;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const Item im = items[it];
+        const uint32_t h = im.halo;
+        const uint32_t nf = pl.nfine[h];
+        if (nf == 0) continue;
+        const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
+        const double R = ha.rung_r[h];
+        const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
+        const int32_t hidx = (int32_t)ha.index[h];
+        uint32_t* fc = fine_cnt + pl.fine_off[h];
+        const int64_t* fex = FILL ? fine_excl + pl.fine_off[h] : nullptr;
+        const bool dmo = cfg.dmo != 0;
+        sweep_item(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+            if (!ok || v.grnr[t] != hidx) return;
+            const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
+            if (!(r2 <= r2max)) return;
+            const Part p = rel_part(v, t, cx, cy, cz, halfL);
+            const double q0 = ax == 0 ? p.y : p.x, q1 = ax == 2 ? p.y : p.z;
+            const double rp = sqrt(__dadd_rn(__dmul_rn(q0, q0), __dmul_rn(q1, q1)));  // projected_aperture_properties.py:122-127
+            const uint32_t fb = fine_bin(rp, R, nf);
+            if (!FILL) {
+                atomicAdd(&fc[fb], 1u);
+            } else {
+                Rec rc;
+                rc.rbits = (unsigned long long)__double_as_longlong(rp);
+                rc.m = v.mass[t];
+                rc.flags = dmo ? 1u : (uint32_t)v.type[t];
+                const uint32_t slot = atomicAdd(&fc[fb], 1u);  // fc is the zeroed cursor array here
+                recs[(unsigned long long)fex[fb] + slot] = rc;
+            }
+        });
+    }
+}
+
+// One CTA per halo: per-type running sums over the halo's records sorted by
+// projected radius; writes HalfMassRadius{Gas,Dm,Star} of every aperture of axis ax.
+__global__ void __launch_bounds__(256) k_pj_scan(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ acc_list,
+                                                 const unsigned int* __restrict__ n_acc, PjPlan pl, int ax,
+                                                 const int64_t* __restrict__ fine_excl,
+                                                 const Rec* __restrict__ recs) {
+    constexpr int NT = 256, K = 4, NG = 3;
+    __shared__ double wsum[NT / 32][NG];
+    __shared__ double carry[NG];
+    __shared__ double thr[SOAP_MAX_APERTURES][NG];
+    __shared__ double cap_r[SOAP_MAX_APERTURES][NG], cap_in[SOAP_MAX_APERTURES][NG], cap_ex[SOAP_MAX_APERTURES][NG];
+    __shared__ uint32_t cap_i[SOAP_MAX_APERTURES][NG];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int npj = cfg.n_pj;
+    for (unsigned int it = blockIdx.x; it < *n_acc; it += gridDim.x) {
+        const uint32_t h = acc_list[it];
+        const uint32_t nf = pl.nfine[h];
+        if (nf == 0) continue;
+        const uint32_t fo = pl.fine_off[h];
+        const unsigned long long e0 = (unsigned long long)fine_excl[fo];
+        const uint32_t n = (uint32_t)((unsigned long long)fine_excl[fo + nf] - e0);
+        const Rec* R = recs + e0;
+        double* row = ha.out + (int64_t)h * ha.ncol;
+        __syncthreads();
+        if ((int)threadIdx.x < npj * NG) {
+            const int p = threadIdx.x / NG, g = threadIdx.x % NG;
+            // half the mass of type g inside aperture p of this projection (written by k_projected);
+            // block columns 4.. are the masses of type codes gas, dm, star, bh
+            thr[p][g] = 0.5 * row[cfg.lay.pj[p] + ax * PJ_BLOCK + 4 + g];
+            cap_i[p][g] = 0xffffffffu;
+        }
+        if (threadIdx.x < NG) carry[threadIdx.x] = 0.0;
+        __syncthreads();
+        for (uint32_t t0 = 0; t0 < n; t0 += NT * K) {
+            const uint32_t i0 = t0 + threadIdx.x * K;
+            Rec rc[K];
+            double loc[NG] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (i0 + k < n) {
+                    rc[k] = R[i0 + k];
+#pragma unroll
+                    for (int g = 0; g < NG; g++)
+                        if ((rc[k].flags & 3u) == (uint32_t)g) loc[g] += (double)rc[k].m;
+                } else {
+                    rc[k].rbits = 0; rc[k].m = 0.f; rc[k].flags = 3u;
+                }
+            }
+            double ex[NG];
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                double x = loc[g];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                if (lane == 31) wsum[wid][g] = x;
+                ex[g] = x - loc[g];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                double b = carry[g];
+                for (int w = 0; w < wid; w++) b += wsum[w][g];
+                ex[g] += b;
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t i = i0 + k;
+                if (i >= n) break;
+                const uint32_t g = rc[k].flags & 3u;
+                if (g >= (uint32_t)NG) continue;
+                const double m = (double)rc[k].m;
+                const double cex = ex[g], cin = cex + m;
+                ex[g] = cin;
+                // half_mass_radius.py:63: first record of the type with cumulative weight >= target
+                for (int p = 0; p < npj; p++)
+                    if (thr[p][g] > 0.0 && cin >= thr[p][g] && !(cex >= thr[p][g])) {
+                        cap_r[p][g] = __longlong_as_double((long long)rc[k].rbits);
+                        cap_in[p][g] = cin; cap_ex[p][g] = cex; cap_i[p][g] = i;
+                    }
+            }
+            __syncthreads();
+            if (threadIdx.x < NG) {
+                double b = carry[threadIdx.x];
+                for (int w = 0; w < NT / 32; w++) b += wsum[w][threadIdx.x];
+                carry[threadIdx.x] = b;
+            }
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < npj * NG) {
+            const int p = threadIdx.x / NG, g = threadIdx.x % NG;
+            double hm = 0.0;
+            const uint32_t i = cap_i[p][g];
+            if (thr[p][g] > 0.0 && i != 0xffffffffu) {
+                const double rmax_ = cap_r[p][g], Wmax = cap_in[p][g], Wmin = cap_ex[p][g];
+                double rmin_ = 0.0;
+                for (uint32_t j = i; j-- > 0;)
+                    if ((R[j].flags & 3u) == (uint32_t)g) {
+                        rmin_ = __longlong_as_double((long long)R[j].rbits);
+                        break;
+                    }
+                // half_mass_radius.py:64-80
+                if (Wmin == Wmax) hm = 0.5 * (rmin_ + rmax_);
+                else hm = rmin_ + (thr[p][g] - Wmin) / (Wmax - Wmin) * (rmax_ - rmin_);
+            }
+            row[cfg.lay.pj[p] + ax * PJ_BLOCK + 18 + g] = hm;
         }
         __syncthreads();
     }
@@ -748,6 +933,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += small_ctr[t].candidates;
     }
     c->last_small_pairs = (int64_t)total_pairs;
+    for (int t = 0; t < NTIER; t++) c->last_tier_pairs[t] = (int64_t)small_ctr[t].pairs;
     const bool trace = getenv("SOAP_B200_TRACE") != nullptr;
     if (trace)
         fprintf(stderr, "[soap_b200] tiers: lists %u %u %u -> general %u | small pairs %llu %llu %llu\n", 0u, 0u, 0u, n_pend,
@@ -839,7 +1025,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                 // bins first: they feed the bucket lists of the CTA-wide kernels below
                 const unsigned int nb = (hc.n_fine + 7) / 8;
                 LAUNCH(h, k_sort_bins, nb < (unsigned)(sm * 8) ? nb : (unsigned)(sm * 8), 256, 0, stream, fine_excl,
-                       hc.n_fine, ctr, recs, bkt_big, bkt_huge);
+                       hc.n_fine, ctr, 1, recs, bkt_big, bkt_huge);
             }
             {
                 unsigned int gs = (unsigned)(max_bkt < (size_t)(sm * 16) ? max_bkt : (size_t)(sm * 16));
@@ -877,6 +1063,45 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             log.begin("moments", stream);
             if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
             if (soap_launch_projected(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
+            if (dc.n_pj > 0 && (dc.flags & PF_HMR)) {
+                // projected half-mass radii: per axis bin by projected radius, sort the bins, scan
+                // (timed inside the enclosing "moments" phase)
+                PjPlan pl;
+                pl.nfine = (uint32_t*)h->get("h_pj_nfine", sizeof(uint32_t) * (size_t)H);
+                pl.fine_off = (uint32_t*)h->get("h_pj_fine_off", sizeof(uint32_t) * (size_t)H);
+                pl.n_fine = (unsigned int*)h->get("h_pj_nf", sizeof(unsigned int) * 4);
+                if (!pl.nfine || !pl.fine_off || !pl.n_fine) return -1;
+                CUDA_TRY(cudaMemsetAsync(pl.n_fine, 0, sizeof(unsigned int) * 4, stream));
+                LAUNCH(h, k_pj_plan, grid_for(n_try, 128), 128, 0, stream, ha, dc, acc_list, &ctr->n_acc, pl);
+                unsigned int nfp = 0;
+                CUDA_TRY(cudaMemcpyAsync(&nfp, pl.n_fine, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                if (nfp > 0) {
+                    uint32_t* pcnt = (uint32_t*)h->get("h_pj_cnt", sizeof(uint32_t) * (size_t)(nfp + 1));
+                    int64_t* pexcl = (int64_t*)h->get("h_pj_excl", sizeof(int64_t) * (size_t)(nfp + 1));
+                    // bound particles of the accepted halos: at most the records of this rung
+                    Rec* precs = (Rec*)h->get("h_pj_recs", sizeof(Rec) * (size_t)(hc.rec_total + 1));
+                    if (!pcnt || !pexcl || !precs) return -1;
+                    for (int ax = 0; ax < 3; ax++) {
+                        CUDA_TRY(cudaMemsetAsync(pcnt, 0, sizeof(uint32_t) * (nfp + 1), stream));
+                        LAUNCH(h, k_pj_bins<false>, sweep_grid, TB, 0, stream, v, ha, dc, items, &ctr->n_items, pl, ax,
+                               pcnt, pexcl, precs);
+                        if (soap_exclusive_scan_u32(h, pcnt, nullptr, pexcl, nfp + 1, nullptr, stream)) return -1;
+                        CUDA_TRY(cudaMemsetAsync(pcnt, 0, sizeof(uint32_t) * (nfp + 1), stream));
+                        LAUNCH(h, k_pj_bins<true>, sweep_grid, TB, 0, stream, v, ha, dc, items, &ctr->n_items, pl, ax,
+                               pcnt, pexcl, precs);
+                        CUDA_TRY(cudaMemsetAsync(&ctr->n_bkt_small, 0, 3 * sizeof(unsigned int), stream));
+                        const unsigned int nb = (nfp + 7) / 8;
+                        LAUNCH(h, k_sort_bins, nb < (unsigned)(sm * 8) ? nb : (unsigned)(sm * 8), 256, 0, stream, pexcl,
+                               nfp, ctr, 0, precs, bkt_big, bkt_huge);
+                        LAUNCH(h, (k_sort_bucket<SB_CAP, 512>), (unsigned)(sm * 3), 512, SB_CAP * sizeof(Rec), stream,
+                               bkt_big, &ctr->n_bkt_big, precs);
+                        LAUNCH(h, (k_sort_bucket<0, 512>), 64, 512, 16, stream, bkt_huge, &ctr->n_bkt_huge, precs);
+                        LAUNCH(h, k_pj_scan, n_try < (unsigned)(sm * 4) ? n_try : (unsigned)(sm * 4), 256, 0, stream, ha, dc,
+                               acc_list, &ctr->n_acc, pl, ax, pexcl, precs);
+                    }
+                }
+            }
             if (soap_launch_kappa(c, dc, ha, items, &ctr->n_items, hc.n_items, acc_list, &ctr->n_acc, n_try, sweep_grid,
                                   stream))
                 return -1;

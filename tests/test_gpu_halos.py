@@ -75,7 +75,7 @@ def test_dummy_chunk_projected_apertures():
     data, H = synth.dummy_chunk(127, 30, boxsize=L, n_background=50000,
                                 npart_choices=(1, 10, 100, 1000, 5000))
     pj = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3) for kpc in (10.0, 30.0, 50.0, 100.0)]
-    _run(data, H, cp, SO4[:1], [], flags=0, dmo=False, projected=pj)
+    _run(data, H, cp, SO4[:1], [], flags=8, dmo=False, projected=pj)
 
 
 def test_read_radius_too_small_status():
