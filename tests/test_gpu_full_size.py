@@ -1,0 +1,108 @@
+"""Full-size checks of the CUDA path on BASELINE config 2 (512^3 particles, 2e5
+halos) through properties that need no oracle run, plus the cross-check that
+the three execution tiers (fused warp tiers, fused CTA tier, general path)
+implement one semantics."""
+
+import os
+
+import numpy as np
+import pytest
+
+from soap_b200 import synth
+from tests import _compare as cmp
+
+pytestmark = pytest.mark.gpu
+
+SO4 = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
+
+
+def _process(data, halos, cp, L, no_tiers=False, fine_ppc=0):
+    from soap_b200.halo_tasks import DeviceChunk, process_halos
+
+    cfg = cmp.device_config(cp, so=SO4, flags=8, dmo=True)
+    if no_tiers:
+        os.environ["SOAP_B200_NO_TIERS"] = "1"
+    try:
+        chunk = DeviceChunk(data, L, fine_ppc=fine_ppc)
+        res = process_halos(chunk, cfg, halos)
+        out = {n: res.get(n).copy() for n in res.names()}
+        st = res.status.cpu().numpy()
+        pairs = chunk.last_pairs()
+        chunk.free()
+    finally:
+        os.environ.pop("SOAP_B200_NO_TIERS", None)
+    return out, st, pairs
+
+
+def _assert_same(a, b, int_keys):
+    for k in a:
+        x, y = a[k], b[k]
+        if k.split("/")[-1] in int_keys:
+            assert np.array_equal(x, y), k
+        else:
+            sc = np.maximum(np.abs(y), 1e-30)
+            # sums are accumulated in a different order per tier: float64 round-off only
+            bad = np.abs(x - y) > 1e-9 * sc + 1e-9 * np.nanmax(np.abs(y))
+            assert not bad.any(), (k, np.argwhere(bad)[:5], x[bad][:5], y[bad][:5])
+
+
+INT_KEYS = {"status", "n_loop", "n_pairs", "Ngas", "Ndm", "Nstar", "Nbh", "radius"}
+
+
+def test_tiers_and_general_path_agree():
+    """every halo through the fused tiers == every halo through the general path"""
+    L = 60.0
+    cp = synth.coordinate_unit_params(L)
+    data, halos = synth.nfw_chunk(1500000, 3000, L, seed=21, device="cuda", max_np=100000)
+    a, sa, pa = _process(data, halos, cp, L)
+    b, sb, pb = _process(data, halos, cp, L, no_tiers=True)
+    assert np.array_equal(sa, sb) and pa == pb
+    _assert_same(a, b, INT_KEYS)
+
+
+def test_config2_full_size_invariants():
+    import torch
+
+    n_part, n_halos, L, max_np = 512**3, 200000, 284.4, 2.0e6
+    cp = synth.coordinate_unit_params(L)
+    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=20261018, device="cuda", max_np=max_np)
+    out, st, pairs = _process(data, halos, cp, L)
+    assert np.all((st == 0) | (st == 1)), np.unique(st)
+    ok = st == 0
+    assert ok.sum() > 0.99 * n_halos
+    nb = halos["nr_bound_part"].cpu().numpy()
+    cen = halos["is_central"].cpu().numpy() == 1
+    # every bound particle is inside the accepted sphere (subhalo_properties.py:2632-2646)
+    assert np.all(out["BoundSubhalo/Ndm"][ok] == nb[ok])
+    assert np.all(out["InputHalos/n_pairs"][ok] >= nb[ok])
+    assert pairs == int(out["InputHalos/n_pairs"][ok].sum())
+    # the accepted radius is a rung of the 1.2x ladder above the input search radius
+    sr = halos["search_radius"].cpu().numpy()
+    rung = np.log(out["InputHalos/radius"][ok] / sr[ok]) / np.log(1.2)
+    nl = out["InputHalos/n_loop"][ok]
+    assert np.all(nl >= 1)
+    capped = np.isclose(out["InputHalos/radius"][ok], halos["read_radius"].cpu().numpy()[ok])
+    assert np.all(np.abs(rung - (nl - 1))[~capped] < 1e-6)
+    # SO: M = 4/3 pi R^3 rho_ref exactly as computed (SO_properties.py:212-215); nested radii
+    rho = [cmp.device_config(cp, so=SO4).so_reference_density(i) for i in range(4)]
+    c = ok & cen
+    for i in range(4):
+        r, m = out[f"SO/{i}/r"][c], out[f"SO/{i}/Mso"][c]
+        has = r > 0
+        assert has.mean() > 0.99
+        assert np.allclose(m[has], 4.0 / 3.0 * np.pi * r[has] ** 3 * rho[i], rtol=1e-12)
+        # mass counted inside the sphere: mean density of the particles brackets the threshold
+        assert np.all(out[f"SO/{i}/Ndm"][c][has] >= 1)
+    r200c, r200m, r500c = out["SO/0/r"][c], out["SO/1/r"][c], out["SO/2/r"][c]
+    both = (r200c > 0) & (r200m > 0) & (r500c > 0)
+    assert np.all(r500c[both] <= r200c[both]) and np.all(r200c[both] <= r200m[both])
+    # satellites have no SO (SO_properties.py:3627)
+    assert np.all(out["SO/0/r"][ok & ~cen] == 0.0)
+    # half-mass radius inside the enclosing radius (tests/test_half_mass_radius.py:31)
+    assert np.all(out["BoundSubhalo/HalfMassRadiusTot"][ok] <= out["BoundSubhalo/EncloseRadius"][ok])
+    # idempotence: a second pass over the same chunk gives the same table
+    out2, st2, pairs2 = _process(data, halos, cp, L)
+    assert np.array_equal(st, st2) and pairs == pairs2
+    _assert_same(out, out2, INT_KEYS)
+    del data, halos
+    torch.cuda.empty_cache()
