@@ -944,7 +944,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         if (c->last_rounds > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
         CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
         // ladder look-ahead: the first round covers 4 rungs per sweep, stragglers more
-        const int look = c->last_rounds == 1 ? 4 : (c->last_rounds == 2 ? 6 : LOOK_MAX);
+        const int look = c->last_rounds == 1 ? 4 : LOOK_MAX;
         // plan a sweep per halo of `list`; coarse meshes / huge spheres can need more
         // work items than provisioned: grow the list and plan again
         auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int replan) -> int {

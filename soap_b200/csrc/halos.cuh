@@ -146,7 +146,7 @@ struct HaloArrays {
     double* rung_msum;         // [H][LOOK_MAX] their mass
 };
 
-constexpr int LOOK_MAX = 8;  // ladder rungs one count sweep can cover
+constexpr int LOOK_MAX = 12;  // ladder rungs one count sweep can cover
 
 // A work item = a contiguous range [first, first+count) of a halo's candidate
 // stream (its rows concatenated in row order).  row0 / pos0 locate the first

@@ -619,7 +619,9 @@ __global__ void __launch_bounds__(512, 1) k_small_warps(ChunkView v, HaloArrays 
         align_bar();
         // ============ phase 3: scans and solves (two more alignment barriers inside)
         if (state == WS_TRY) {
-            scan_solve_halo<NCH, 1, 32, SMALL_K, true>(W.S, ha, cfg, h, n, W.rec, nullptr, ctr, &W.minr, &W.minfof, 1u);
+            // tiles of 64 records for the smallest spheres: more lanes busy per pass
+            scan_solve_halo<NCH, 1, 32, (CAP <= 256 ? 2 : SMALL_K), true>(W.S, ha, cfg, h, n, W.rec, nullptr, ctr, &W.minr,
+                                                                          &W.minfof, 1u);
             __syncwarp();
         } else {
             align_bar();
