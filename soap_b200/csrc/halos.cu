@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
 // shared_mesh.py:122-200), for the next ha.look[h] ladder rungs in one sweep:
 // the sphere of the furthest rung is swept once and every particle is binned by
 // the first rung whose radius includes it (the same r2 <= radius^2 test).
-__global__ void __launch_bounds__(TB) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
+__global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
                                               Counters* ctr) {
     __shared__ SweepShared S;
     __shared__ unsigned int s_cnt[TB / 32][LOOK_MAX];

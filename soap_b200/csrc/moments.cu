@@ -27,7 +27,7 @@ namespace {
 constexpr int TB = SWEEP_NT;
 
 template <int V, int NTY>
-__global__ void __launch_bounds__(TB) k_moments(ChunkView v, HaloArrays ha, DevCfg cfg,
+__global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(ChunkView v, HaloArrays ha, DevCfg cfg,
                                                 const Item* __restrict__ items,
                                                 const unsigned int* __restrict__ n_items_dev,
                                                 double* __restrict__ gbanks, int gbank_stride, int priv) {
