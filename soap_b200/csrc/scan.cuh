@@ -412,6 +412,8 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         // softened radii: isclose(max(soft, r), 0) needs soft <= 1e-8
         double min_soft = fmin(fmin(cfg.soft[0], cfg.soft[1]), fmin(cfg.soft[2], cfg.soft[3]));
         const uint32_t nskip_s = (min_soft <= 1e-8) ? fnc_u : 0u;
+        double so_rho_max = 0.0;
+        for (int q = 0; q < n_so; q++) so_rho_max = fmax(so_rho_max, cfg.so_rho[q]);
 
         // ------------------------------------------------------------ pass B
         if (gt < NCH) { S.carry[gt] = S.carry_in[gt]; S.carryc[gt] = S.carryc_in[gt]; }
@@ -445,6 +447,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) { b0[ch] = base[ch]; bc0[ch] = basec[ch]; }
             // detection sweep
+            const uint32_t seen_nn = S.tidx[T_NONNEG], seen_hm0 = S.tidx[T_SUBHMR];  // stale values are safe (atomicMin)
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const uint32_t i = i0 + k;
@@ -461,25 +464,28 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 for (int ch = 0; ch < NCH; ch++)
                     if (c == ch) { base[ch] += m; basec[ch]++; }
                 const double call_in = call_ex + m;
-                // SO first-below (SO_properties.py:140-147)
-                if (i >= nskip_so) {
-                    float cm = so_cm32(call_in, r, cfg.nu);
-                    double dens = so_density(cm, r);
-                    for (int q = 0; q < n_so; q++)
-                        if (!(dens > cfg.so_rho[q]) && i < S.tidx[T_SO + (q)]) atomicMin(&S.tidx[T_SO + (q)], i);
-                    if (!(cm < 0.f) && i < S.tidx[T_NONNEG]) atomicMin(&S.tidx[T_NONNEG], i);
+                // SO first-below (SO_properties.py:140-147).  Records whose density is far above
+                // every threshold (the bulk of a halo) skip the exact division.
+                if (n_so > 0 && i >= nskip_so) {
+                    const float cm = so_cm32(call_in, r, cfg.nu);
+                    const double vol = 4.0 / 3.0 * SOAP_PI * (r * r * r);
+                    if (!((double)cm > so_rho_max * vol * (1.0 + 1e-9))) {
+                        const double dens = (double)cm / vol;  // SO_properties.py:420
+                        for (int q = 0; q < n_so; q++)
+                            if (!(dens > cfg.so_rho[q]) && i < S.tidx[T_SO + (q)]) atomicMin(&S.tidx[T_SO + (q)], i);
+                    }
+                    if (i < seen_nn && !(cm < 0.f)) atomicMin(&S.tidx[T_NONNEG], i);
                 }
                 if (bound) {
                     const double cb_in = cb_ex + m;
-                    // Vmax of the bound subhalo (subhalo_properties.py:982-1045)
+                    // Vmax of the bound subhalo (subhalo_properties.py:982-1045); a record that cannot
+                    // reach this thread's running maximum skips the division
                     if (cfg.do_sub) {
-                        if (posb >= nskip_u && r > 0.0) amU.offer(cb_in / r, r, i);
+                        if (posb >= nskip_u && r > 0.0 && cb_in >= amU.v * r - 1e-12 * fabs(amU.v * r)) amU.offer(cb_in / r, r, i);
                         double rs = fmax(cfg.soft[tc], r);
-                        if (posb >= nskip_s && rs > 0.0) amS.offer(cb_in / rs, rs, i);
+                        if (posb >= nskip_s && rs > 0.0 && cb_in >= amS.v * rs - 1e-12 * fabs(amS.v * rs)) amS.offer(cb_in / rs, rs, i);
                         // half-mass radii (half_mass_radius.py:63)
-                        if (want_hmr || true) {
-                            if (cb_in >= 0.5 * Mb_g[0] && i < S.tidx[T_SUBHMR + (0)]) atomicMin(&S.tidx[T_SUBHMR + (0)], i);
-                        }
+                        if (i < seen_hm0 && cb_in >= 0.5 * Mb_g[0]) atomicMin(&S.tidx[T_SUBHMR + (0)], i);
                         if (want_hmr) {
 #pragma unroll
                             for (int g = 0; g < 4; g++)
@@ -496,54 +502,72 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                     if (want_hmr && r > cfg.ap_r[a] && i < S.tidx[T_APEDGE + (a)]) atomicMin(&S.tidx[T_APEDGE + (a)], i);
             }
             gsync<NT>();
-            // capture sweep: the owner of a newly found index re-derives its values
+            // capture: the thread whose records hold a newly found index re-derives its values
             {
-                double bb[NCH];
+                auto mine = [&](uint32_t idx) { return idx >= i0 && idx < i0 + K && idx < n; };
+                // exclusive class prefix at record i0 + kk of this thread
+                auto prefix_at = [&](int kk, double (&ex)[NCH]) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) bb[ch] = b0[ch];
+                    for (int ch = 0; ch < NCH; ch++) ex[ch] = b0[ch];
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const uint32_t i = i0 + k;
-                    if (i >= n) break;
-                    const double r = __longlong_as_double((long long)rc[k].rbits);
-                    const double m = (double)rc[k].m;
-                    const int c = rec_class<NCH>(rc[k].flags);
-                    const uint32_t tc = NCH == 2 ? 1u : (rc[k].flags & 3u);
-                    const double call_ex = all_sum<NCH>(bb);
-                    double ex[NCH];
+                    for (int k = 0; k < K; k++)
+                        if (k < kk) {
+                            const int c = rec_class<NCH>(rc[k].flags);
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ch++) ex[ch] = bb[ch];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                        if (c == ch) bb[ch] += m;
-                    for (int q = 0; q < n_so; q++)
-                        if (S.tidx[T_SO + (q)] == i) {
-                            S.tcap[T_SO + (q)][0] = r; S.tcap[T_SO + (q)][1] = call_ex + m; S.tcap[T_SO + (q)][2] = call_ex;
+                            for (int ch = 0; ch < NCH; ch++)
+                                if (c == ch) ex[ch] += (double)rc[k].m;
                         }
-                    if (S.tidx[T_NONNEG] == i) {
-                        S.tcap[T_NONNEG][0] = r;
-                        S.tcap[T_NONNEG][1] = (double)so_cm32(call_ex + m, r, cfg.nu);
+                };
+                auto rec_at = [&](int kk, double& r, double& m, uint32_t& tc, int& c) {
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (k == kk) {
+                            r = __longlong_as_double((long long)rc[k].rbits);
+                            m = (double)rc[k].m;
+                            tc = NCH == 2 ? 1u : (rc[k].flags & 3u);
+                            c = rec_class<NCH>(rc[k].flags);
+                        }
+                };
+                auto capture = [&](int target, int kind, int g) {
+                    const uint32_t idx = S.tidx[target];
+                    if (!mine(idx)) return;
+                    const int kk = (int)(idx - i0);
+                    double ex[NCH], in[NCH], r = 0.0, m = 0.0;
+                    uint32_t tc = 0;
+                    int c = 0;
+                    prefix_at(kk, ex);
+                    rec_at(kk, r, m, tc, c);
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) in[ch] = ex[ch] + (c == ch ? m : 0.0);
+                    const double call_ex = all_sum<NCH>(ex);
+                    if (kind == 0) {  // SO crossing
+                        S.tcap[target][0] = r; S.tcap[target][1] = call_ex + m; S.tcap[target][2] = call_ex;
+                    } else if (kind == 1) {  // first non-negative cumulative mass
+                        S.tcap[target][0] = r;
+                        S.tcap[target][1] = (double)so_cm32(call_ex + m, r, cfg.nu);
+                    } else if (kind == 2) {  // bound half mass, all types
+                        S.tcap[target][0] = r;
+                        S.tcap[target][1] = bound_sum<NCH>(in);
+                        S.tcap[target][2] = bound_sum<NCH>(ex);
+                    } else if (kind == 3) {  // bound half mass of group g
+                        if (in_group(g, tc)) {
+                            S.tcap[target][0] = r;
+                            S.tcap[target][1] = group_sum<NCH>(in, g, true);
+                            S.tcap[target][2] = group_sum<NCH>(ex, g, true);
+                        }
+                    } else {  // aperture edge: class sums in front of it
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ch++) S.tcap[target][ch] = ex[ch];
                     }
-                    if (cfg.do_sub) {
-                        if (S.tidx[T_SUBHMR + (0)] == i) {
-                            S.tcap[T_SUBHMR + (0)][0] = r;
-                            S.tcap[T_SUBHMR + (0)][1] = bound_sum<NCH>(bb);
-                            S.tcap[T_SUBHMR + (0)][2] = bound_sum<NCH>(ex);
-                        }
-                        if (want_hmr)
-                            for (int g = 0; g < 4; g++)
-                                if (S.tidx[T_SUBHMR + (1 + g)] == i && in_group(g, tc)) {
-                                    S.tcap[T_SUBHMR + (1 + g)][0] = r;
-                                    S.tcap[T_SUBHMR + (1 + g)][1] = group_sum<NCH>(bb, g, true);
-                                    S.tcap[T_SUBHMR + (1 + g)][2] = group_sum<NCH>(ex, g, true);
-                                }
-                    }
-                    for (int a = 0; a < n_ap; a++)
-                        if (S.tidx[T_APEDGE + (a)] == i) {
-#pragma unroll
-                            for (int ch = 0; ch < NCH; ch++) S.tcap[T_APEDGE + (a)][ch] = ex[ch];
-                        }
+                };
+                for (int q = 0; q < n_so; q++) capture(T_SO + q, 0, 0);
+                if (n_so > 0) capture(T_NONNEG, 1, 0);
+                if (cfg.do_sub) {
+                    capture(T_SUBHMR, 2, 0);
+                    if (want_hmr)
+                        for (int g = 0; g < 4; g++) capture(T_SUBHMR + 1 + g, 3, g);
                 }
+                for (int a = 0; a < n_ap; a++) capture(T_APEDGE + a, 4, 0);
             }
             gsync<NT>();
         }
@@ -823,7 +847,8 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 for (int q = 0; q < SOAP_MAX_SO; q++)
                     if (q < n_so && S.so_r_[q] > 0.0) {
                         // Vmax_soft inside the SO (SO_properties.py:573-600)
-                        if (r < S.so_r_[q] && rs > 0.0 && (min_soft > 1e-8 || pos_all >= S.n_zero))
+                        if (r < S.so_r_[q] && rs > 0.0 && (min_soft > 1e-8 || pos_all >= S.n_zero) &&
+                            call_in >= amSO[q].v * rs - 1e-12 * fabs(amSO[q].v * rs))
                             amSO[q].offer(call_in / rs, rs, i);
                         // first dark matter particle outside (SO_properties.py:471-482)
                         if (tc == 1u && r > S.so_r_[q] && i < S.tidx[T_DMOUT + (q)]) atomicMin(&S.tidx[T_DMOUT + (q)], i);
@@ -842,34 +867,50 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
             }
             gsync<NT>();
             {
-                double bb[NCH];
+                auto mine = [&](uint32_t idx) { return idx >= i0 && idx < i0 + K && idx < n; };
+                for (int q = 0; q < n_so; q++) {
+                    const uint32_t idx = S.tidx[T_DMOUT + q];
+                    if (!mine(idx)) continue;
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) bb[ch] = b0[ch];
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const uint32_t i = i0 + k;
-                    if (i >= n) break;
-                    const double r = __longlong_as_double((long long)rc[k].rbits);
-                    const double m = (double)rc[k].m;
-                    const int c = rec_class<NCH>(rc[k].flags);
-                    const uint32_t tc = NCH == 2 ? 1u : (rc[k].flags & 3u);
-                    double ex[NCH];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++) ex[ch] = bb[ch];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                        if (c == ch) bb[ch] += m;
-                    for (int q = 0; q < n_so; q++)
-                        if (S.tidx[T_DMOUT + (q)] == i) { S.tcap[T_DMOUT + (q)][0] = r; S.tcap[T_DMOUT + (q)][1] = m; }
-                    if (want_hmr)
-                        for (int a = 0; a < n_ap; a++)
-                            for (int g = 0; g < 4; g++)
-                                if (S.tidx[T_APHMR + (a) * 4 + (g)] == i && in_group(g, tc)) {
-                                    S.tcap[T_APHMR + (a) * 4 + (g)][0] = r;
-                                    S.tcap[T_APHMR + (a) * 4 + (g)][1] = group_sum<NCH>(bb, g, cfg.ap_incl[a] == 0);
-                                    S.tcap[T_APHMR + (a) * 4 + (g)][2] = group_sum<NCH>(ex, g, cfg.ap_incl[a] == 0);
-                                }
+                    for (int k = 0; k < K; k++)
+                        if (k == (int)(idx - i0)) {
+                            S.tcap[T_DMOUT + q][0] = __longlong_as_double((long long)rc[k].rbits);
+                            S.tcap[T_DMOUT + q][1] = (double)rc[k].m;
+                        }
                 }
+                if (want_hmr)
+                    for (int a = 0; a < n_ap; a++)
+                        for (int g = 0; g < 4; g++) {
+                            const uint32_t idx = S.tidx[T_APHMR + a * 4 + g];
+                            if (!mine(idx)) continue;
+                            const int kk = (int)(idx - i0);
+                            double ex[NCH], in[NCH], r = 0.0;
+                            uint32_t tc = 0;
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++) ex[ch] = b0[ch];
+#pragma unroll
+                            for (int k = 0; k < K; k++) {
+                                const int c = rec_class<NCH>(rc[k].flags);
+                                if (k < kk) {
+#pragma unroll
+                                    for (int ch = 0; ch < NCH; ch++)
+                                        if (c == ch) ex[ch] += (double)rc[k].m;
+                                }
+                                if (k == kk) {
+                                    r = __longlong_as_double((long long)rc[k].rbits);
+                                    tc = NCH == 2 ? 1u : (rc[k].flags & 3u);
+#pragma unroll
+                                    for (int ch = 0; ch < NCH; ch++) in[ch] = (c == ch) ? (double)rc[k].m : 0.0;
+                                }
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++) in[ch] += ex[ch];
+                            if (in_group(g, tc)) {
+                                S.tcap[T_APHMR + a * 4 + g][0] = r;
+                                S.tcap[T_APHMR + a * 4 + g][1] = group_sum<NCH>(in, g, cfg.ap_incl[a] == 0);
+                                S.tcap[T_APHMR + a * 4 + g][2] = group_sum<NCH>(ex, g, cfg.ap_incl[a] == 0);
+                            }
+                        }
             }
             gsync<NT>();
         }
