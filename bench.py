@@ -42,7 +42,12 @@ WORKLOADS = {
     # name: (n_part, n_halos, boxsize, max_np)
     "config2": (512**3, 200000, 284.4, 2.0e6),
     "config2_small": (128**3, 3125, 71.1, 2.0e5),  # same number densities, 1/64 of the volume
+    # hydro variants (BASELINE config 3: gas/DM/stars/BH, exclusive+inclusive 30/50/100 kpc apertures + SO;
+    # "_kappa" adds kappa_corot, which runs on the general path only)
+    "config3": (2 * 256**3, 50000, 142.2, 5.0e5),
+    "config3_kappa": (2 * 256**3, 50000, 142.2, 5.0e5),
 }
+HYDRO_TYPES = {0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001}
 SEED = 20261018
 SO_LIST = None  # filled in main (needs synth)
 
@@ -229,9 +234,18 @@ def size_sample_and_time(data_np, H_np, L, cp, so_list, cores, budget_s):
 # ------------------------------------------------------------------ GPU arm
 
 
-def build_config(cp, so_list):
-    from soap_b200.halo_tasks import HaloPropConfig, PF_HMR
+def build_config(cp, so_list, workload="config2"):
+    from soap_b200.halo_tasks import HaloPropConfig, PF_HMR, PF_KAPPA, PF_KIN, PF_TENS
 
+    if workload.startswith("config3"):
+        aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 50.0, 100.0) for incl in (0, 1)]
+        flags = PF_KIN | PF_TENS | PF_HMR | (PF_KAPPA if workload.endswith("kappa") else 0)
+        return HaloPropConfig(
+            boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
+            mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
+            H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
+            nu_density=cp["nu_density"], phys_mpc_to_coord=cp["phys_mpc_to_coord"],
+            do_subhalo=True, so=list(so_list), apertures=aps, property_flags=flags, dmo=False)
     return HaloPropConfig(
         boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
         mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
@@ -266,8 +280,13 @@ def main():
     so_list = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
     n_part, n_halos, L, max_np = WORKLOADS[args.workload]
     cp = synth.coordinate_unit_params(L)
-    wl_name = (f"{args.workload}: synthetic DMO chunk, {n_part} particles, {n_halos} halos, L={L} Mpc, "
-               "SO 200_crit/200_mean/500_crit/BN98 + BoundSubhalo (MINIMAL_FLAMINGO)")
+    if args.workload.startswith("config3"):
+        wl_name = (f"{args.workload}: synthetic hydro chunk (gas/DM/stars/BH), {n_part} particles, {n_halos} halos, "
+                   f"L={L} Mpc, exclusive+inclusive 30/50/100 kpc apertures + SO x4 + BoundSubhalo, kinematics, "
+                   "tensors, half-mass radii")
+    else:
+        wl_name = (f"{args.workload}: synthetic DMO chunk, {n_part} particles, {n_halos} halos, L={L} Mpc, "
+                   "SO 200_crit/200_mean/500_crit/BN98 + BoundSubhalo (MINIMAL_FLAMINGO)")
     have_cuda = torch.cuda.is_available()
     gen_dev = f"cuda:{local_rank}" if have_cuda else "cpu"
     if have_cuda:
@@ -275,7 +294,9 @@ def main():
     cores = os.cpu_count() or 1
 
     t0 = time.time()
-    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank, device=gen_dev, max_np=max_np)
+    hydro = args.workload.startswith("config3")
+    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank + (1 if hydro else 0), device=gen_dev, max_np=max_np,
+                                  type_fractions=HYDRO_TYPES if hydro else None)
     if have_cuda:
         torch.cuda.synchronize()
     log(f"[bench] rank {rank}: generated {args.workload} on {gen_dev} in {time.time() - t0:.1f}s")
@@ -324,7 +345,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = torch.device(f"cuda:{local_rank}")
     handle = _lib.default_handle(local_rank)
-    cfg = build_config(cp, so_list)
+    cfg = build_config(cp, so_list, args.workload)
     ncol, cols = result_layout(cfg.to_c())
     H = int(halos["cofp"].shape[0])
     table = torch.empty((H, ncol), dtype=torch.float64, device=dev)

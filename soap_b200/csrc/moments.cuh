@@ -165,9 +165,9 @@ __device__ inline void build_cuts(Cuts& c, const DevCfg& cfg, const ScanRes* sr,
     for (int a = 0; a < cfg.n_ap; a++)
         if (ap_c(a)) add_cut(c, cfg.ap_r[a], 0, nullptr);
     if (sub_c && (cfg.flags & PF_TENS)) add_cut(c, 10.0 * sr->sub_hmr[0], 0, nullptr);
-    for (int q = 0; q < SOAP_MAX_SO; q++) c.pos_so[q] = so_c(q) ? find_cut(c, sr->so_r[q], 1) : -1;
+    for (int q = 0; q < n_so; q++) c.pos_so[q] = so_c(q) ? find_cut(c, sr->so_r[q], 1) : -1;  // read for q < n_so only
     c.pos_vmax = (sub_c && sr->sub_vmax_s_r > 0.0) ? find_cut(c, sr->sub_vmax_s_r, 0) : -1;
-    for (int a = 0; a < SOAP_MAX_APERTURES; a++) c.pos_ap[a] = ap_c(a) ? find_cut(c, cfg.ap_r[a], 0) : -1;
+    for (int a = 0; a < cfg.n_ap; a++) c.pos_ap[a] = ap_c(a) ? find_cut(c, cfg.ap_r[a], 0) : -1;
     c.pos_tens = (sub_c && (cfg.flags & PF_TENS)) ? find_cut(c, 10.0 * sr->sub_hmr[0], 0) : -1;
 }
 

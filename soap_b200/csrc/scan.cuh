@@ -73,6 +73,9 @@ struct ScanShared {
     double required_;
     double so_r_[SOAP_MAX_SO];
     int commit_lo_, commit_hi_;
+    // per-SO solve results (computed by one lane each)
+    int par_fail[SOAP_MAX_SO], par_status[SOAP_MAX_SO];
+    double par_r[SOAP_MAX_SO], par_mass[SOAP_MAX_SO];
     double ap_thr[SOAP_MAX_APERTURES][4];
     // argmax block reduce
     double am_v[NT / 32], am_r[NT / 32];
@@ -592,7 +595,70 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         gsync<NT>();
 
         if (ALIGN) align_bar();
-        // ------------------------- rank 0, thread 0: SO solve + checks
+        // ------------- rank 0: the SO solves, one lane per SO variation (they are independent;
+        // the sequential commit logic below consumes them in halo_prop_list order)
+        if (crank == 0 && gt < n_so) {
+            const int q = gt;
+            const double r_last = n > 0 ? __longlong_as_double((long long)R[n - 1].rbits) : 0.0;
+            const double rho = cfg.so_rho[q];
+            double SO_r = 0.0, SO_mass = 0.0;
+            int fail = 0, status = SOAP_HALO_OK;
+            const uint32_t nr_parts = n > nskip_so ? n - nskip_so : 0u;
+            if (nr_parts > 0) {
+                uint32_t i = S.tidx[T_SO + (q)];
+                if (i == NONE) {
+                    // no particle below the threshold (SO_properties.py:147-156)
+                    if (r_last > cfg.r20) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
+                    else { fail = 1; }
+                } else if (i == nskip_so) {
+                    // all below: SO_properties.py:157-177
+                    uint32_t ip = S.tidx[T_NONNEG];
+                    if (ip == NONE) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
+                    else {
+                        double rp = S.tcap[T_NONNEG][0], cmp = S.tcap[T_NONNEG][1];
+                        SO_r = sqrt(0.75 * cmp / (SOAP_PI * rp * rho));
+                        SO_mass = cmp * SO_r / rp;
+                    }
+                } else {
+                    // intersecting interval (SO_properties.py:180-201)
+                    double r2 = S.tcap[T_SO + (q)][0];
+                    double cum2 = S.tcap[T_SO + (q)][1], cum1 = S.tcap[T_SO + (q)][2];
+                    double r1 = __longlong_as_double((long long)R[i - 1].rbits);
+                    float M1 = so_cm32(cum1, r1, cfg.nu), M2 = so_cm32(cum2, r2, cfg.nu);
+                    bool ab1 = so_density(M1, r1) > rho, ab2 = so_density(M2, r2) > rho;
+                    double cum = cum2;
+                    bool ran_out = false;
+                    while (r1 == r2 || ab1 == ab2) {
+                        i++;
+                        if (i >= n) { ran_out = true; break; }
+                        r1 = r2; M1 = M2; ab1 = ab2;
+                        r2 = __longlong_as_double((long long)R[i].rbits);
+                        cum += (double)R[i].m;
+                        M2 = so_cm32(cum, r2, cfg.nu);
+                        ab2 = so_density(M2, r2) > rho;
+                    }
+                    if (ran_out) {
+                        if (r_last > cfg.r20) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
+                        else { fail = 1; }
+                    } else {
+                        // SO_properties.py:206-215 (float32 M promoted to float64)
+                        double dM1 = (double)M1, dM2 = (double)M2;
+                        double rho_dim = rho * (r1 * r1 * r1) / dM1;
+                        double slope_dim = (dM2 - dM1) / (r2 - r1) * (r1 / dM1);
+                        double root;
+                        if (brentq_dev(1.0, r2 / r1, rho_dim, slope_dim, &root)) {
+                            fail = 2; status = SOAP_HALO_ROOT_FAILED;
+                        } else {
+                            SO_r = r1 * root;
+                            SO_mass = 4.0 / 3.0 * SOAP_PI * (SO_r * SO_r * SO_r) * rho;
+                        }
+                    }
+                }
+            }
+            S.par_fail[q] = fail; S.par_status[q] = status; S.par_r[q] = SO_r; S.par_mass[q] = SO_mass;
+        }
+        gsync<NT>();
+        // ------------------------- rank 0, thread 0: commit logic + checks
         if (gt == 0 && crank == 0) {
             {
                 // innermost particle over the halo's work items (SO_properties.py:407-409)
@@ -626,60 +692,9 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 } else if (p < off_ap) {
                     const int q = p - off_so;
                     if (central) {
-                const double rho = cfg.so_rho[q];
-                double SO_r = 0.0, SO_mass = 0.0;
-                const uint32_t nr_parts = n > nskip_so ? n - nskip_so : 0u;
-                if (nr_parts > 0) {
-                    uint32_t i = S.tidx[T_SO + (q)];
-                    if (i == NONE) {
-                        // no particle below the threshold (SO_properties.py:147-156)
-                        if (r_last > cfg.r20) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
-                        else { fail = 1; required = 0.0; }
-                    } else if (i == nskip_so) {
-                        // all below: SO_properties.py:157-177
-                        uint32_t ip = S.tidx[T_NONNEG];
-                        if (ip == NONE) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
-                        else {
-                            double rp = S.tcap[T_NONNEG][0], cmp = S.tcap[T_NONNEG][1];
-                            SO_r = sqrt(0.75 * cmp / (SOAP_PI * rp * rho));
-                            SO_mass = cmp * SO_r / rp;
-                        }
-                    } else {
-                        // intersecting interval (SO_properties.py:180-201)
-                        double r2 = S.tcap[T_SO + (q)][0];
-                        double cum2 = S.tcap[T_SO + (q)][1], cum1 = S.tcap[T_SO + (q)][2];
-                        double r1 = __longlong_as_double((long long)R[i - 1].rbits);
-                        float M1 = so_cm32(cum1, r1, cfg.nu), M2 = so_cm32(cum2, r2, cfg.nu);
-                        bool ab1 = so_density(M1, r1) > rho, ab2 = so_density(M2, r2) > rho;
-                        double cum = cum2;
-                        bool ran_out = false;
-                        while (r1 == r2 || ab1 == ab2) {
-                            i++;
-                            if (i >= n) { ran_out = true; break; }
-                            r1 = r2; M1 = M2; ab1 = ab2;
-                            r2 = __longlong_as_double((long long)R[i].rbits);
-                            cum += (double)R[i].m;
-                            M2 = so_cm32(cum, r2, cfg.nu);
-                            ab2 = so_density(M2, r2) > rho;
-                        }
-                        if (ran_out) {
-                            if (r_last > cfg.r20) { fail = 2; status = SOAP_HALO_SO_NOT_FOUND; }
-                            else { fail = 1; required = 0.0; }
-                        } else {
-                            // SO_properties.py:206-215 (float32 M promoted to float64)
-                            double dM1 = (double)M1, dM2 = (double)M2;
-                            double rho_dim = rho * (r1 * r1 * r1) / dM1;
-                            double slope_dim = (dM2 - dM1) / (r2 - r1) * (r1 / dM1);
-                            double root;
-                            if (brentq_dev(1.0, r2 / r1, rho_dim, slope_dim, &root)) {
-                                fail = 2; status = SOAP_HALO_ROOT_FAILED;
-                            } else {
-                                SO_r = r1 * root;
-                                SO_mass = 4.0 / 3.0 * SOAP_PI * (SO_r * SO_r * SO_r) * rho;
-                            }
-                        }
-                    }
-                }
+                const int sf = S.par_fail[q];
+                double SO_r = S.par_r[q], SO_mass = S.par_mass[q];
+                if (sf) { fail = sf; status = S.par_status[q]; required = 0.0; }
                 if (!fail) {
                     sr->so_r[q] = SO_r;
                     sr->so_mass[q] = SO_mass;
