@@ -254,7 +254,30 @@ def build_config(cp, so_list, workload="config2"):
         do_subhalo=True, so=list(so_list), apertures=[], property_flags=PF_HMR, dmo=True)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries underneath (NCCL prints its version banner to stdout) must not add lines to
+    the one-JSON-line contract: send file descriptor 1 to stderr and keep the real one aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -330,7 +353,7 @@ def main():
             "gpu_launches": 0,
             "note": "reference = numpy oracle port (the reference needs unyt/mpi4py/h5py/virgo, absent here)",
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -525,7 +548,7 @@ def main():
             "stats": {k: int(v) for k, v in sorted(stats.items())}, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
