@@ -59,8 +59,9 @@ struct Bucket {
 // (small.cu) takes halos with up to lim[t] bound particles, the rest goes to
 // the general path.  tier_n = device counters of the four lists.
 struct TierLims { long long lim[3]; };
-__global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_t* list1, uint32_t* list2,
-                       uint32_t* pend, unsigned int* tier_n, TierLims tl) {
+constexpr int TIER_BUCKETS = 1024;  // one bucket per nr_bound_part value handled by a fused tier
+__global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* pend, unsigned int* tier_n, unsigned int* size_hist,
+                       TierLims tl) {
     int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
     ha.cur_r[h] = ha.sr_in[h];
@@ -71,13 +72,53 @@ __global__ void k_init(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_t* lis
     ha.commit_lo[h] = 0;
     ha.commit_hi[h] = 0;
     ha.mslot[h] = -1;
+    // the fused tiers take their halos largest first and size-sorted (k_tier_place): the warps
+    // of a lock-step CTA then work on halos of similar size
     const long long ne = ha.nexp[h];
-    if (ne <= tl.lim[0]) list0[atomicAdd(&tier_n[0], 1u)] = (uint32_t)h;
-    else if (ne <= tl.lim[1]) list1[atomicAdd(&tier_n[1], 1u)] = (uint32_t)h;
-    else if (ne <= tl.lim[2]) list2[atomicAdd(&tier_n[2], 1u)] = (uint32_t)h;
+    if (ne <= tl.lim[2]) atomicAdd(&size_hist[TIER_BUCKETS - 1 - (ne < 0 ? 0 : (int)ne)], 1u);
     else pend[atomicAdd(&tier_n[3], 1u)] = (uint32_t)h;
     double* row = ha.out + h * ha.ncol;
     for (int64_t c = 0; c < ha.ncol; c++) row[c] = 0.0;
+}
+
+// exclusive scan of the size histogram (descending size) + the tier list sizes
+__global__ void k_tier_scan(unsigned int* size_hist, unsigned int* tier_n, TierLims tl) {
+    __shared__ unsigned int sh[TIER_BUCKETS];
+    const int t = threadIdx.x;
+    const unsigned int v = size_hist[t];
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < TIER_BUCKETS; o <<= 1) {
+        unsigned int x = t >= o ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += x;
+        __syncthreads();
+    }
+    size_hist[t] = sh[t] - v;  // position of the first halo of this size among all fused-tier halos
+    if (t < 3) {
+        // bucket b holds nr_bound_part = TIER_BUCKETS - 1 - b; tier k takes lim[k-1] < ne <= lim[k]
+        const long long hi = tl.lim[t], lo = t == 0 ? -1 : tl.lim[t - 1];
+        unsigned int cnt = 0;
+        if (hi > lo) {
+            const int b0 = TIER_BUCKETS - 1 - (int)hi, b1 = TIER_BUCKETS - 1 - (int)(lo + 1);  // inclusive bucket range
+            cnt = sh[b1] - (b0 > 0 ? sh[b0 - 1] : 0u);
+        }
+        tier_n[t] = cnt;
+    }
+}
+
+__global__ void k_tier_place(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_t* list1, uint32_t* list2,
+                             unsigned int* size_cursor, const unsigned int* __restrict__ size_hist, TierLims tl) {
+    int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    const long long ne = ha.nexp[h];
+    if (ne > tl.lim[2]) return;
+    const int b = TIER_BUCKETS - 1 - (ne < 0 ? 0 : (int)ne);
+    const unsigned int pos = size_hist[b] + atomicAdd(&size_cursor[b], 1u);  // among all tier halos, largest first
+    // a tier's list starts where its largest size starts
+    if (ne <= tl.lim[0]) list0[pos - size_hist[TIER_BUCKETS - 1 - (int)tl.lim[0]]] = (uint32_t)h;
+    else if (ne <= tl.lim[1]) list1[pos - size_hist[TIER_BUCKETS - 1 - (int)tl.lim[1]]] = (uint32_t)h;
+    else list2[pos - size_hist[TIER_BUCKETS - 1 - (int)tl.lim[2]]] = (uint32_t)h;
 }
 
 // ------------------------------------------------------------- k_plan_items
@@ -902,7 +943,16 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             prev = tl.lim[t];
         }
     }
-    LAUNCH(h, k_init, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, list0, list1, list2, pend, tier_n, tl);
+    for (int t = 0; t < NTIER; t++)
+        if (tl.lim[t] >= TIER_BUCKETS) SOAP_FAIL("soap_process_halos: tier limit above %d", TIER_BUCKETS - 1);
+    WS_GET(size_hist, unsigned int, h, "h_size_hist", 2 * TIER_BUCKETS);
+    CUDA_TRY(cudaMemsetAsync(size_hist, 0, 2 * TIER_BUCKETS * sizeof(unsigned int), stream));
+    LAUNCH(h, k_init, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, pend, tier_n, size_hist, tl);
+    if (tl.lim[NTIER - 1] >= 0) {
+        LAUNCH(h, k_tier_scan, 1, TIER_BUCKETS, 0, stream, size_hist, tier_n, tl);
+        LAUNCH(h, k_tier_place, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, list0, list1, list2,
+               size_hist + TIER_BUCKETS, size_hist, tl);
+    }
     for (int t = 0; t < NTIER; t++) {
         if (!tier_on[t]) continue;
         int to = t + 1;  // overflow goes to the next enabled tier, else to the general path
