@@ -132,11 +132,12 @@ typedef struct {
     double ap_radius[SOAP_MAX_APERTURES];     /* coordinate units */
     double ap_physical_mpc[SOAP_MAX_APERTURES];
     int ap_inclusive[SOAP_MAX_APERTURES];
-    int n_projected;
-    double proj_radius[SOAP_MAX_APERTURES];
+    int n_projected;                          /* ProjectedAperture radii, ascending (needs do_subhalo) */
+    double proj_radius[SOAP_MAX_APERTURES];   /* coordinate units */
     double proj_physical_mpc[SOAP_MAX_APERTURES];
-    /* property groups: bit 0 kinematics (veldisp, L), bit 1 kappa_corot / DtoT,
-     * bit 2 non-iterative inertia tensors, bit 3 half-mass radii per type */
+    /* property groups: bit 0 kinematics (veldisp, L), bit 1 kappa_corot / DtoT and the stellar
+     * rotational velocity / cylindrical dispersions (needs bit 0), bit 2 non-iterative inertia
+     * tensors, bit 3 half-mass radii per type (also the projected ones) */
     uint32_t property_flags;
     int dmo;                  /* only dark matter present / requested */
 } soap_halo_config;
@@ -144,7 +145,7 @@ typedef struct {
 /* Column layout of the result table for a config: writes a '\n'-separated list
  * of "name:width" into buf (host) and returns the total number of float64
  * columns (or <0).  Names follow the reference's output groups
- * ("BoundSubhalo/...", "SO/<i>/...", "Aperture/<i>/..."). */
+ * ("BoundSubhalo/...", "SO/<i>/...", "Aperture/<i>/...", "ProjectedAperture/<i>/proj{x,y,z}/..."). */
 int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t buflen);
 
 /* process_halos: SOAP/core/halo_tasks.py:276-430 with process_single_halo

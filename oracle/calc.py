@@ -17,6 +17,11 @@ Restates (unyt stripped, thresholds pre-converted):
                            SOAP/property_calculation/inertia_tensors.py:19-132
   * get_weighted_projected_inertia_tensor
                            inertia_tensors.py:226-343
+  * build_rotation_matrix / calculate_cylindrical_velocities
+                           SOAP/property_calculation/cylindrical_coordinates.py:13-93
+  * get_rotation_velocity_mass_weighted,
+    get_cylindrical_velocity_dispersion_vector_mass_weighted
+                           kinematic_properties.py:17-51,130-178
 """
 
 import numpy as np
@@ -346,3 +351,51 @@ def get_weighted_projected_inertia_tensor(
             tensor.fill(0)
             break
     return np.concatenate([np.diag(tensor), [tensor[(0, 1)]]])
+
+
+# ------------------------------------------------------- cylindrical velocities
+
+
+def build_rotation_matrix(z_target):
+    """cylindrical_coordinates.py:13-42."""
+    z_axis = z_target / np.linalg.norm(z_target)
+    helper = np.array([1, 0, 0])
+    if np.allclose(z_axis, helper / np.linalg.norm(helper), rtol=0.1):
+        helper = np.array([0, 1, 0])
+    x_axis = np.cross(helper, z_axis)
+    x_axis /= np.linalg.norm(x_axis)
+    y_axis = np.cross(z_axis, x_axis)
+    return np.vstack([x_axis, y_axis, z_axis])
+
+
+def calculate_cylindrical_velocities(
+    positions, velocities, z_target, reference_position=None, reference_velocity=None
+):
+    """cylindrical_coordinates.py:45-93: (v_r, v_phi, v_z) per particle."""
+    prel = positions if reference_position is None else positions - reference_position
+    vrel = velocities if reference_velocity is None else velocities - reference_velocity
+    R = build_rotation_matrix(z_target)
+    positions_rot = prel @ R.T
+    velocities_rot = vrel @ R.T
+    x, y = positions_rot[:, 0], positions_rot[:, 1]
+    vx, vy, vz = velocities_rot[:, 0], velocities_rot[:, 1], velocities_rot[:, 2]
+    phi = np.arctan2(y, x)
+    v_r = vx * np.cos(phi) + vy * np.sin(phi)
+    v_phi = -vx * np.sin(phi) + vy * np.cos(phi)
+    return np.stack([v_r, v_phi, vz], axis=1)
+
+
+def get_rotation_velocity_mass_weighted(particle_masses, particle_azimuthal_velocities):
+    """kinematic_properties.py:17-51."""
+    mass_weights = particle_masses / particle_masses.sum()
+    return (mass_weights * particle_azimuthal_velocities).sum()
+
+
+def get_cylindrical_velocity_dispersion_vector_mass_weighted(
+    particle_masses, particle_cylindrical_velocities
+):
+    """kinematic_properties.py:130-178: [sigma_r, sigma_phi, sigma_z]."""
+    w = particle_masses / particle_masses.sum()
+    mean_velocity = (w[:, None] * particle_cylindrical_velocities).sum(axis=0)
+    squared = (w[:, None] * (particle_cylindrical_velocities - mean_velocity) ** 2).sum(axis=0)
+    return np.sqrt(squared)

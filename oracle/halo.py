@@ -39,6 +39,9 @@ from .calc import (
     get_velocity_dispersion_matrix,
     get_angular_momentum,
     get_angular_momentum_and_kappa_corot_mass_weighted,
+    calculate_cylindrical_velocities,
+    get_rotation_velocity_mass_weighted,
+    get_cylindrical_velocity_dispersion_vector_mass_weighted,
     get_vmax,
     get_weighted_inertia_tensor,
     get_weighted_projected_inertia_tensor,
@@ -112,6 +115,21 @@ def _kin_block(mass, pos, vel, centre, params, with_kappa):
     else:
         out["L"] = get_angular_momentum(mass, pos, vel, ref_velocity=out["vcom"])
     return out
+
+
+def _star_cylindrical(res, mass, pos, vel):
+    """StellarRotationalVelocity and the cylindrical dispersions
+    (aperture_properties.py:1477-1536, subhalo_properties.py:1410-1470): stars in
+    the frame of their own angular momentum, velocities about vcom_star."""
+    if len(mass) < 2 or "Lstar" not in res or np.sum(res["Lstar"]) == 0:
+        return
+    cyl = calculate_cylindrical_velocities(pos, vel, np.asarray(res["Lstar"], dtype=np.float64),
+                                           reference_velocity=res["vcom_star"])
+    res["StellarRotationalVelocity"] = get_rotation_velocity_mass_weighted(mass, cyl[:, 1])
+    sig = get_cylindrical_velocity_dispersion_vector_mass_weighted(mass, cyl)
+    res["StellarCylindricalVelocityDispersion"] = np.sqrt((sig**2).sum() / 3)
+    res["StellarCylindricalVelocityDispersionVertical"] = sig[2]
+    res["StellarCylindricalVelocityDispersionDiscPlane"] = np.sqrt((sig[:2] ** 2).sum())
 
 
 def _store_group(res, prefix, blk, with_kappa):
@@ -432,6 +450,7 @@ class SubhaloOracle:
             s = types == t
             blk = _kin_block(mass[s], position[s], velocity[s], centre, p, kap)
             _store_group(res, nm, blk, kap)
+        _star_cylindrical(res, mass[star], position[star], velocity[star])
         s = gas | star
         blk = _kin_block(mass[s], position[s], velocity[s], centre, p, True)
         if blk is not None:
@@ -519,6 +538,7 @@ class ApertureOracle:
             s = types == t
             blk = _kin_block(mass[s], position[s], velocity[s], centre, p, kap)
             _store_group(res, nm, blk, kap)
+        _star_cylindrical(res, mass[star], position[star], velocity[star])
         s = gas | star
         blk = _kin_block(mass[s], position[s], velocity[s], centre, p, True)
         if blk is not None:

@@ -815,6 +815,9 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
         if (cfg->property_flags & PF_KAPPA) {
             add(p + "kappa_corot_gas", 1); add(p + "kappa_corot_star", 1); add(p + "kappa_corot_baryons", 1);
             add(p + "DtoTgas", 1); add(p + "DtoTstar", 1);
+            add(p + "StellarRotationalVelocity", 1); add(p + "StellarCylindricalVelocityDispersion", 1);
+            add(p + "StellarCylindricalVelocityDispersionVertical", 1);
+            add(p + "StellarCylindricalVelocityDispersionDiscPlane", 1); add(p + "kappa_scratch", 2);
         }
         if (cfg->property_flags & PF_TENS) {
             add(p + (kind == 2 ? "StellarInertiaTensorNoniterative" : "TotalInertiaTensorNoniterative"), 6);

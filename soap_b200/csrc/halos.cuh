@@ -43,7 +43,7 @@ __host__ __device__ inline BlockLayout block_layout(uint32_t flags, int n_extra)
     b.kin = (flags & PF_KIN) ? o : -1;
     if (flags & PF_KIN) o += 51;
     b.kappa = (flags & PF_KAPPA) ? o : -1;
-    if (flags & PF_KAPPA) o += 5;
+    if (flags & PF_KAPPA) o += 11;  // kappa x3, DtoT x2, stellar rotation + cylindrical dispersions x4, 2 scratch
     b.tens = (flags & PF_TENS) ? o : -1;
     if (flags & PF_TENS) o += 12;
     b.hmr = (flags & PF_HMR) ? o : -1;

@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
 struct KapSel {
     double vc[3][3], lh[3][3];  // per group: reference velocity, unit angular momentum
     int ok[3];
+    double ex[3], ey[3];  // in-plane axes of the stellar frame (cylindrical_coordinates.py:13-42)
+    int cyl_ok;           // Nstar >= 2 and sum(Lstar) != 0 (aperture_properties.py:1483-1490)
     double R;
     int incl, is_sub;
-    double* out;  // the block's 5 kappa slots
+    double* out;  // the block's 11 kappa / rotation slots
 };
 
 __device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl) {
@@ -160,13 +162,30 @@ __device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl)
         for (int d = 0; d < 3; d++) k.lh[g][d] = nrm > 0.0 ? L[d] / nrm : 0.0;
     }
     k.out = blk + bl.kappa;
+    // stellar frame: z = L_star / |L_star|, x = helper x z normalised, y = z x x
+    {
+        const double* o = kin + 30;
+        const double Lx = o[6], Ly = o[7], Lz = o[8];
+        k.cyl_ok = blk[2] >= 2.0 && (Lx + Ly + Lz) != 0.0 && k.ok[1];
+        const double* z = k.lh[1];
+        // np.allclose(z_axis, [1, 0, 0], rtol=0.1): |z - h| <= 1e-8 + 0.1 |h| per component
+        const bool near_x = fabs(z[0] - 1.0) <= 1e-8 + 0.1 && fabs(z[1]) <= 1e-8 && fabs(z[2]) <= 1e-8;
+        const double hx = near_x ? 0.0 : 1.0, hy = near_x ? 1.0 : 0.0, hz = 0.0;
+        double x[3] = {hy * z[2] - hz * z[1], hz * z[0] - hx * z[2], hx * z[1] - hy * z[0]};
+        const double xn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        for (int d = 0; d < 3; d++) k.ex[d] = xn > 0.0 ? x[d] / xn : 0.0;
+        k.ey[0] = z[1] * k.ex[2] - z[2] * k.ex[1];
+        k.ey[1] = z[2] * k.ex[0] - z[0] * k.ex[2];
+        k.ey[2] = z[0] * k.ex[1] - z[1] * k.ex[0];
+        if (!(xn > 0.0)) k.cyl_ok = 0;  // the reference divides by zero here (L anti-parallel to x)
+    }
 }
 
 __global__ void __launch_bounds__(TB) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
                                               const unsigned int* __restrict__ n_items_dev) {
     __shared__ SweepShared SW;
     __shared__ KapSel sel[1 + SOAP_MAX_APERTURES];
-    __shared__ double acc[1 + SOAP_MAX_APERTURES][5];
+    __shared__ double acc[1 + SOAP_MAX_APERTURES][11];
     __shared__ int nsel;
     const unsigned int n_items = *n_items_dev;
     for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(TB) k_kappa(ChunkView v, HaloArrays ha, DevCfg
                 }
             nsel = n;
         }
-        for (int i = threadIdx.x; i < (1 + SOAP_MAX_APERTURES) * 5; i += TB) (&acc[0][0])[i] = 0.0;
+        for (int i = threadIdx.x; i < (1 + SOAP_MAX_APERTURES) * 11; i += TB) (&acc[0][0])[i] = 0.0;
         __syncthreads();
         const int ns = nsel;
         if (ns == 0) continue;
@@ -230,12 +249,27 @@ __global__ void __launch_bounds__(TB) k_kappa(ChunkView v, HaloArrays ha, DevCfg
                     if (Ri2 != 0.0 && Li > 0.0) atomicAdd(&acc[s][g], 0.5 * (Li * Li / (m * Ri2)));
                     if (g < 2 && Li < 0.0) atomicAdd(&acc[s][3 + g], m);
                 }
+                if (tc == 2u && k.cyl_ok) {
+                    // cylindrical velocity of a star in the frame of L_star, about vcom_star
+                    // (calculate_cylindrical_velocities, cylindrical_coordinates.py:45-93)
+                    const double ux = vx - k.vc[1][0], uy = vy - k.vc[1][1], uz = vz - k.vc[1][2];
+                    const double X = x * k.ex[0] + y * k.ex[1] + z * k.ex[2];
+                    const double Y = x * k.ey[0] + y * k.ey[1] + z * k.ey[2];
+                    const double VX = ux * k.ex[0] + uy * k.ex[1] + uz * k.ex[2];
+                    const double VY = ux * k.ey[0] + uy * k.ey[1] + uz * k.ey[2];
+                    const double VZ = ux * k.lh[1][0] + uy * k.lh[1][1] + uz * k.lh[1][2];
+                    const double Rp = sqrt(X * X + Y * Y);
+                    const double cph = Rp > 0.0 ? X / Rp : 1.0, sph = Rp > 0.0 ? Y / Rp : 0.0;  // arctan2(0, 0) = 0
+                    const double vr = VX * cph + VY * sph, vp = -VX * sph + VY * cph;
+                    atomicAdd(&acc[s][5], m * vr); atomicAdd(&acc[s][6], m * vp); atomicAdd(&acc[s][7], m * VZ);
+                    atomicAdd(&acc[s][8], m * vr * vr); atomicAdd(&acc[s][9], m * vp * vp); atomicAdd(&acc[s][10], m * VZ * VZ);
+                }
             }
         });
         __syncthreads();
-        for (int i = threadIdx.x; i < ns * 5; i += TB) {
-            const double a = acc[i / 5][i % 5];
-            if (a != 0.0) atomicAdd(&sel[i / 5].out[i % 5], a);
+        for (int i = threadIdx.x; i < ns * 11; i += TB) {
+            const double a = acc[i / 11][i % 11];
+            if (a != 0.0) atomicAdd(&sel[i / 11].out[i % 11], a);
         }
         __syncthreads();
     }
@@ -275,6 +309,22 @@ __global__ void k_kappa_finish(HaloArrays ha, DevCfg cfg, const uint32_t* __rest
         o[2] = Kb > 0.0 ? kc_b / Kb : 0.0;
         o[3] = Mg != 0.0 ? 1.0 - 2.0 * mc_g / Mg : 0.0;
         o[4] = Ms != 0.0 ? 1.0 - 2.0 * mc_s / Ms : 0.0;
+        // stellar rotation and cylindrical dispersions (kinematic_properties.py:17-51,130-178;
+        // aperture_properties.py:1502-1536): mean v_phi, sqrt(sum sigma^2 / 3), sigma_z, sqrt(sigma_r^2 + sigma_phi^2)
+        {
+            double mean[3], var[3];
+            const bool have = Ms != 0.0 && (o[5] != 0.0 || o[6] != 0.0 || o[7] != 0.0 || o[8] != 0.0 || o[9] != 0.0 || o[10] != 0.0);
+            for (int c = 0; c < 3; c++) {
+                mean[c] = have ? o[5 + c] / Ms : 0.0;
+                var[c] = have ? fmax(o[8 + c] / Ms - mean[c] * mean[c], 0.0) : 0.0;
+            }
+            o[5] = mean[1];
+            o[6] = sqrt((var[0] + var[1] + var[2]) / 3.0);
+            o[7] = sqrt(var[2]);
+            o[8] = sqrt(var[0] + var[1]);
+            o[9] = 0.0;
+            o[10] = 0.0;
+        }
     };
     if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
     for (int a = 0; a < cfg.n_ap; a++)

@@ -224,6 +224,10 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
                 # kappa_corot / DtoT are ratios of second moments: absolute tolerance
                 for k in ("kappa_corot_gas", "kappa_corot_star", "kappa_corot_baryons", "DtoTgas", "DtoTstar"):
                     rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_SECOND, scale=1.0)
+                # stellar rotation / cylindrical dispersions: velocities, scale = typical particle speed
+                for k in ("StellarRotationalVelocity", "StellarCylindricalVelocityDispersion",
+                          "StellarCylindricalVelocityDispersionVertical", "StellarCylindricalVelocityDispersionDiscPlane"):
+                    rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_SECOND, scale=300.0)
             if flags & 4:
                 tn = "StellarInertiaTensor" if kind == "ap" else "TotalInertiaTensor"
                 for suffix in ("Noniterative", "ReducedNoniterative"):

@@ -338,6 +338,33 @@ def gen_tensors(out):
     out["ten_n"] = k
 
 
+def gen_cyl(out):
+    nsc = load("SOAP/property_calculation/cylindrical_coordinates.py",
+               ["build_rotation_matrix", "calculate_cylindrical_velocities"])
+    nsk = load("SOAP/property_calculation/kinematic_properties.py",
+               ["get_weighted_rotation_velocity", "get_rotation_velocity_mass_weighted",
+                "get_weighted_cylindrical_velocity_dispersion_vector",
+                "get_cylindrical_velocity_dispersion_vector_mass_weighted"])
+    rng = np.random.default_rng(19)
+    k = 0
+    for n, zt in ((2, [0.0, 0.0, 2.0]), (50, [1.0, 0.02, 0.0]), (400, [0.3, -0.5, 0.8]), (3000, [-1.0, 0.3, 0.1])):
+        m = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        pos = rng.normal(size=(n, 3)) * 0.01
+        pos[0] = 0.0  # a particle on the axis: phi = arctan2(0, 0)
+        vel = (rng.normal(size=(n, 3)) * 80).astype(np.float32)
+        zt = np.array(zt)
+        vref = (m[:, None] * vel).sum(axis=0) / m.sum()
+        cyl = nsc["calculate_cylindrical_velocities"](ua(pos), ua(vel), ua(zt), reference_velocity=ua(vref))
+        out[f"cyl{k}_m"], out[f"cyl{k}_pos"], out[f"cyl{k}_vel"], out[f"cyl{k}_z"] = m, pos, vel, zt
+        out[f"cyl{k}_vref"] = np.asarray(vref)
+        out[f"cyl{k}_cyl"] = np.asarray(cyl)
+        out[f"cyl{k}_R"] = np.asarray(nsc["build_rotation_matrix"](ua(zt)))
+        out[f"cyl{k}_vrot"] = float(nsk["get_rotation_velocity_mass_weighted"](ua(m), ua(np.asarray(cyl)[:, 1])))
+        out[f"cyl{k}_sig"] = np.asarray(nsk["get_cylindrical_velocity_dispersion_vector_mass_weighted"](ua(m), ua(np.asarray(cyl))))
+        k += 1
+    out["cyl_n"] = k
+
+
 def gen_mesh(out):
     ns = load("SOAP/core/shared_mesh.py", ["SharedMesh"])
     SharedMesh = ns["SharedMesh"]
@@ -374,7 +401,7 @@ def main():
     if not os.path.isdir(REF):
         sys.exit("make_golden.py needs /root/reference (build container only)")
     for name, gen in (("so_radius", gen_so), ("half_mass_radius", gen_hmr), ("kinematics", gen_kin),
-                      ("inertia_tensors", gen_tensors), ("shared_mesh", gen_mesh)):
+                      ("inertia_tensors", gen_tensors), ("cylindrical", gen_cyl), ("shared_mesh", gen_mesh)):
         out = {}
         gen(out)
         path = os.path.join(OUT, f"{name}.npz")

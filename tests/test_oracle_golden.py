@@ -88,6 +88,17 @@ def test_inertia_tensors_match_reference(reduced, iters):
     assert some
 
 
+def test_cylindrical_velocities_match_reference():
+    g = _load("cylindrical")
+    for i in range(int(g["cyl_n"])):
+        m, pos, vel, zt, vref = (g[f"cyl{i}_{k}"] for k in ("m", "pos", "vel", "z", "vref"))
+        assert np.array_equal(oc.build_rotation_matrix(zt), g[f"cyl{i}_R"])
+        cyl = oc.calculate_cylindrical_velocities(pos, vel, zt, reference_velocity=vref)
+        assert np.array_equal(cyl, g[f"cyl{i}_cyl"])
+        assert float(oc.get_rotation_velocity_mass_weighted(m, cyl[:, 1])) == float(g[f"cyl{i}_vrot"])
+        assert np.array_equal(oc.get_cylindrical_velocity_dispersion_vector_mass_weighted(m, cyl), g[f"cyl{i}_sig"])
+
+
 def test_shared_mesh_matches_reference():
     g = _load("shared_mesh")
     L = float(g["mesh_L"])
