@@ -8,6 +8,7 @@
 // histogram (the atomic's return value is the particle's rank in its cell) ->
 // exclusive scan -> scatter.  HBM-bound integer work; no tensor cores.
 #include "common.cuh"
+#include "radix.cuh"
 
 thread_local char g_soap_err[512] = "";
 
@@ -76,60 +77,43 @@ struct MeshGeom {
     int res;
 };
 
-__global__ void __launch_bounds__(TB) k_cell_hist(const double* __restrict__ pos, int64_t n,
-                                                  MeshGeom g, int32_t* __restrict__ key,
-                                                  uint32_t* __restrict__ rank,
-                                                  uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(TB) k_cell_key(const double* __restrict__ pos, int64_t n, MeshGeom g,
+                                                 int32_t* __restrict__ cell_idx, uint32_t* __restrict__ key,
+                                                 uint32_t* __restrict__ val) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int cx = cell_coord(pos[3 * i], g.pmin[0], g.cs[0], g.res);
     int cy = cell_coord(pos[3 * i + 1], g.pmin[1], g.cs[1], g.res);
     int cz = cell_coord(pos[3 * i + 2], g.pmin[2], g.cs[2], g.res);
-    int32_t c = cx + g.res * cy + g.res * g.res * cz;
-    key[i] = c;
-    rank[i] = atomicAdd(&count[c], 1u);
+    const int32_t c = cx + g.res * cy + g.res * g.res * cz;  // shared_mesh.py:73-77
+    if (cell_idx) cell_idx[i] = c;
+    key[i] = (uint32_t)c;
+    val[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(TB) k_scatter_idx(const int32_t* __restrict__ key,
-                                                    const uint32_t* __restrict__ rank,
-                                                    const int64_t* __restrict__ offset, int64_t n,
-                                                    int64_t* __restrict__ sort_idx) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    sort_idx[offset[key[i]] + rank[i]] = i;
+// cell_offset[c] = first sorted position with key >= c; cell_count from consecutive offsets
+// (np.bincount + exclusive cumsum of shared_mesh.py:80-102)
+__global__ void __launch_bounds__(TB) k_cell_bounds(const uint32_t* __restrict__ key, uint32_t n, uint32_t ncell,
+                                                    int64_t* __restrict__ offset_ext) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const long long prev = i == 0 ? -1ll : (long long)key[i - 1];
+    const long long cur = i == n ? (long long)ncell : (long long)key[i];
+    for (long long c = prev + 1; c <= cur; c++) offset_ext[c] = i;
 }
 
-__global__ void __launch_bounds__(TB) k_u32_to_i64(const uint32_t* __restrict__ in, int64_t n,
-                                                   int64_t* __restrict__ out) {
+__global__ void __launch_bounds__(TB) k_cell_counts(const int64_t* __restrict__ offset_ext, int64_t ncell,
+                                                    int64_t* __restrict__ count, int64_t* __restrict__ offset) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    offset[c] = offset_ext[c];
+    count[c] = offset_ext[c + 1] - offset_ext[c];
+}
+
+__global__ void __launch_bounds__(TB) k_widen_idx(const uint32_t* __restrict__ in, int64_t n,
+                                                  int64_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
-}
-
-// Stable order: sort every cell's segment of sort_idx ascending.  One CTA per
-// cell; segments up to SEG_CAP in shared memory, longer ones in place in
-// global memory (correct but slow -- only reference-sized cells holding more
-// than SEG_CAP particles take that path).
-constexpr int SEG_CAP = 4096;
-
-struct LessI64 {
-    __device__ __forceinline__ bool operator()(int64_t a, int64_t b) const { return a < b; }
-};
-
-__global__ void __launch_bounds__(TB) k_segment_sort(const int64_t* __restrict__ offset,
-                                                     const uint32_t* __restrict__ count,
-                                                     int64_t* __restrict__ sort_idx) {
-    __shared__ int64_t s[SEG_CAP];
-    const int64_t start = offset[blockIdx.x];
-    const uint32_t cnt = count[blockIdx.x];
-    if (cnt < 2) return;
-    if (cnt <= SEG_CAP) {
-        for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) s[t] = sort_idx[start + t];
-        __syncthreads();
-        block_bitonic_sort(s, cnt, LessI64());
-        for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) sort_idx[start + t] = s[t];
-    } else {
-        block_bitonic_sort(sort_idx + start, cnt, LessI64());
-    }
 }
 
 // ------------------------------------------------------------- sphere query
@@ -317,20 +301,24 @@ int soap_mesh_build(soap_handle* h, const double* pos_dev, int64_t n, int resolu
     MeshGeom g;
     for (int d = 0; d < 3; d++) { g.pmin[d] = pos_min[d]; g.cs[d] = cell_size[d]; }
     g.res = resolution;
-    WS_GET(count32, uint32_t, h, "mesh_count32", ncell);
-    WS_GET(rank, uint32_t, h, "mesh_rank", n);
-    int32_t* key = cell_idx_dev;
-    if (!key) {
-        key = (int32_t*)h->get("mesh_key", sizeof(int32_t) * (size_t)n);
-        if (!key) return -1;
-    }
-    CUDA_TRY(cudaMemsetAsync(count32, 0, sizeof(uint32_t) * ncell, stream));
-    LAUNCH(h, k_cell_hist, grid_for(n, TB), TB, 0, stream, pos_dev, n, g, key, rank, count32);
-    if (soap_exclusive_scan_u32(h, count32, nullptr, cell_offset_dev, ncell, nullptr, stream)) return -1;
-    LAUNCH(h, k_u32_to_i64, grid_for(ncell, TB), TB, 0, stream, count32, ncell, cell_count_dev);
-    LAUNCH(h, k_scatter_idx, grid_for(n, TB), TB, 0, stream, key, rank, cell_offset_dev, n, sort_idx_dev);
-    if (stable)
-        LAUNCH(h, k_segment_sort, (unsigned)ncell, TB, 0, stream, cell_offset_dev, count32, sort_idx_dev);
+    // argsort of the cell ids (shared_mesh.py:105-114): stable LSD radix sort of (cell id, index)
+    // pairs, so sort_idx is ascending within a cell whether or not `stable` is asked for
+    (void)stable;
+    const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    WS_GET(key, uint32_t, h, "mesh_key", n);
+    WS_GET(val, uint32_t, h, "mesh_val", n);
+    WS_GET(key2, uint32_t, h, "mesh_key2", n);
+    WS_GET(val2, uint32_t, h, "mesh_val2", n);
+    WS_GET(ghist, uint32_t, h, "mesh_ghist", (size_t)RS_NB * nblk);
+    WS_GET(offset_ext, int64_t, h, "mesh_offset_ext", ncell + 1);
+    LAUNCH(h, k_cell_key, grid_for(n, TB), TB, 0, stream, pos_dev, n, g, cell_idx_dev, key, val);
+    int bits = 0;
+    while ((1ll << bits) < ncell) bits++;
+    uint32_t *ks = nullptr, *vs = nullptr;
+    if (radix_sort_pairs(h, key, val, key2, val2, ghist, (uint32_t)n, bits, &ks, &vs, stream)) return -1;
+    LAUNCH(h, k_cell_bounds, grid_for(n + 1, TB), TB, 0, stream, ks, (uint32_t)n, (uint32_t)ncell, offset_ext);
+    LAUNCH(h, k_cell_counts, grid_for(ncell, TB), TB, 0, stream, offset_ext, ncell, cell_count_dev, cell_offset_dev);
+    LAUNCH(h, k_widen_idx, grid_for(n, TB), TB, 0, stream, vs, n, sort_idx_dev);
     return 0;
 }
 
