@@ -45,7 +45,7 @@ constexpr int FINE_TARGET = 12;  // expected records per fine radial bin (sorted
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
 // halos with up to this many bound particles start in fused tier 0 / 1 / 2; larger ones take the general path
-constexpr long long SMALL_NEXP_0 = 90, SMALL_NEXP_1 = 200, SMALL_NEXP_2 = 800;
+constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 300, SMALL_NEXP_2 = 800;
 
 struct Bucket {
     unsigned long long start;
@@ -926,7 +926,13 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     uint32_t* next = listB;
     // tiers: fused small-halo kernels first (small.cu), the rest and their overflow below
     constexpr int NTIER = 3;
-    const long long tier_nexp[NTIER] = {SMALL_NEXP_0, SMALL_NEXP_1, SMALL_NEXP_2};
+    long long tier_nexp[NTIER] = {SMALL_NEXP_0, SMALL_NEXP_1, SMALL_NEXP_2};
+    if (const char* e = getenv("SOAP_B200_TIER_NEXP")) {  // tuning switch: "a,b,c"
+        long long a = 0, b = 0, cc = 0;
+        if (sscanf(e, "%lld,%lld,%lld", &a, &b, &cc) == 3 && a <= b && b <= cc && cc < TIER_BUCKETS) {
+            tier_nexp[0] = a; tier_nexp[1] = b; tier_nexp[2] = cc;
+        }
+    }
     uint32_t* tier_list[NTIER + 1];
     WS_GET(list0, uint32_t, h, "h_list0", H); tier_list[0] = list0;
     WS_GET(list1, uint32_t, h, "h_list1", H); tier_list[1] = list1;
