@@ -254,6 +254,27 @@ def build_config(cp, so_list, workload="config2"):
         do_subhalo=True, so=list(so_list), apertures=[], property_flags=PF_HMR, dmo=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the CPU cores of the
+    NUMA node its GPU hangs off, so that N concurrent host->device uploads do not cross sockets."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out  # 0000:xx:yy.z
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 _REAL_STDOUT = None
 
 
@@ -315,6 +336,7 @@ def main():
     if have_cuda:
         torch.cuda.set_device(local_rank)
     cores = os.cpu_count() or 1
+    numa = bind_to_gpu_numa_node(local_rank) if (have_cuda and world > 1 and args.impl == "ours") else None
 
     t0 = time.time()
     hydro = args.workload.startswith("config3")
@@ -472,7 +494,7 @@ def main():
         dt = float(tt.item())
         e2e = {"value": H * world / dt, "unit": "halos/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt,
-               "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i"}
+               "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i", "numa_node": numa}
 
     # -------------------------------------------------------- roofline (rank 0)
     peak, peak_kind = peak_hbm()
