@@ -37,7 +37,6 @@ extern "C" {
 #define SOAP_HALO_COUNT_MISMATCH 2   /* Ntot > nr_bound_part: subhalo_properties.py:2642-2646 (RuntimeError) */
 #define SOAP_HALO_SO_NOT_FOUND 3     /* SO_properties.py:150-153,190-193 (RuntimeError beyond 20 Mpc) */
 #define SOAP_HALO_ROOT_FAILED 4      /* scipy brentq ValueError (same-sign bracket) at SO_properties.py:208 */
-#define SOAP_HALO_INTERNAL_OVERFLOW 5 /* a radial sort bucket exceeded the on-chip capacity (library limit) */
 
 #define SOAP_MAX_SO 8
 #define SOAP_MAX_APERTURES 16

@@ -19,7 +19,7 @@ SOAP_MAX_APERTURES = 16
 SOAP_MAX_PTYPES = 8
 
 # per-halo status codes (include/soap_b200.h)
-HALO_OK, HALO_RADIUS_TOO_SMALL, HALO_COUNT_MISMATCH, HALO_SO_NOT_FOUND, HALO_ROOT_FAILED, HALO_INTERNAL_OVERFLOW = range(6)
+HALO_OK, HALO_RADIUS_TOO_SMALL, HALO_COUNT_MISMATCH, HALO_SO_NOT_FOUND, HALO_ROOT_FAILED = range(5)
 
 
 class SoapError(RuntimeError):

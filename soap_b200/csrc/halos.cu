@@ -890,7 +890,6 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(rec_off, unsigned long long, h, "h_rec_off", H); ha.rec_off = rec_off;
     WS_GET(fine_off, uint32_t, h, "h_fine_off", H); ha.fine_off = fine_off;
     WS_GET(nfine, uint32_t, h, "h_nfine", H); ha.nfine = nfine;
-    WS_GET(required, double, h, "h_required", H); ha.required = required;
     WS_GET(ndone, int32_t, h, "h_ndone", H); ha.ndone = ndone;
     WS_GET(commit_lo, int32_t, h, "h_commit_lo", H); ha.commit_lo = commit_lo;
     WS_GET(commit_hi, int32_t, h, "h_commit_hi", H); ha.commit_hi = commit_hi;

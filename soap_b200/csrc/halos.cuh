@@ -127,7 +127,6 @@ struct HaloArrays {
     unsigned long long* rec_off;
     uint32_t* fine_off;
     uint32_t* nfine;
-    double* required;  // required radius of the failing property of this rung
     int32_t* ndone;    // leading halo_prop_list entries already done (halo_tasks.py:62,121-123)
     int32_t* commit_lo;  // properties [lo, hi) computed at this rung
     int32_t* commit_hi;

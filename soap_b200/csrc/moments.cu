@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         // properties [lo, hi) of halo_prop_list were computed at this rung
         const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
         if (c_hi <= c_lo || ha.status[h] >= 2) continue;
-        const int off_so = cfg.do_sub ? 1 : 0, off_ap = off_so + cfg.n_so;
         const bool sub_c = cfg.do_sub && c_lo == 0;
         const ScanRes* sr = ha.sres + h;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];

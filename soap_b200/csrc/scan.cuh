@@ -379,7 +379,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 const ScanShared<NCH, NT>* P = peer(rk);
                 const double t = P->l_tot[ch];
                 const uint32_t c = P->l_cnt[ch];
-                if (rk < crank) { cin += t; ccin += c; }
+                if (CS > 1 && rk < crank) { cin += t; ccin += c; }
                 tot += t; cnt += c; cnt0 += P->l_cnt0[ch];
                 rmx = fmax(rmx, P->l_rmaxc[ch]);
             }

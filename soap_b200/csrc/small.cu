@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(NT, (V <= 16 ? 512 : 256) / NT > 16 ? 16 : (V 
     __shared__ DimRanges rg[3];
     __shared__ uint32_t row_s0[NT], row_off[NT + 1];
     __shared__ uint32_t w_u32[NW];
-    __shared__ double w_f64[NW];
     __shared__ unsigned long long w_u64[NW];
     __shared__ int32_t w_i32[NW];
     __shared__ SmallCtl B;
@@ -369,21 +368,25 @@ struct __align__(16) WarpSlot {
 
 enum : int { WS_NEED = 0, WS_RUNG = 1, WS_TRY = 2, WS_EXHAUSTED = 3 };
 
-template <int NCH, int V, int CAP>
-__global__ void __launch_bounds__(512, 1) k_small_warps(ChunkView v, HaloArrays ha, DevCfg cfg,
+// MAXW = most warps a CTA is launched with (sets the register budget); gbanks != nullptr: the
+// moment banks of a warp live in global memory (hydro configurations: 4 types x 36 terms per
+// shell do not fit next to the records of enough warps; the banks are touched only on a key change).
+template <int NCH, int V, int CAP, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1) k_small_warps(ChunkView v, HaloArrays ha, DevCfg cfg,
                                                         const uint32_t* __restrict__ list,
                                                         const unsigned int* __restrict__ n_list,
                                                         uint32_t* __restrict__ overflow,
                                                         unsigned int* __restrict__ n_overflow,
                                                         unsigned int* __restrict__ queue_cursor, Counters* ctr,
-                                                        int bank_stride, int slot_bytes) {
+                                                        int bank_stride, int slot_bytes, double* gbanks) {
     constexpr int NTY = NCH == 2 ? 1 : 4;
     constexpr uint32_t CAND_MAX = 64u * CAP;
     using Slot = WarpSlot<NCH, V, CAP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     Slot& W = *(Slot*)(smem_raw + (size_t)wid * slot_bytes);
-    double* banks = (double*)(smem_raw + (size_t)wid * slot_bytes + sizeof(Slot));
+    double* banks = gbanks ? gbanks + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * bank_stride
+                           : (double*)(smem_raw + (size_t)wid * slot_bytes + sizeof(Slot));
     const double L = v.L, halfL = 0.5 * v.L;
     const unsigned int n_total = *n_list;
 
@@ -686,18 +689,31 @@ int launch_warp_tier(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, con
                      unsigned int* queue_cursor, Counters* ctr, int bank_stride, unsigned int n_upper,
                      cudaStream_t stream) {
     soap_handle* h = c->h;
-    const size_t slot = (sizeof(WarpSlot<NCH, V, CAP>) + (size_t)bank_stride * sizeof(double) + 15) & ~(size_t)15;
+    constexpr int MAXW = (NCH == 2 && V <= 16) ? 16 : 8;  // fewer warps, more registers for the wide variants
+    const size_t bank_bytes = (size_t)bank_stride * sizeof(double);
+    size_t slot = (sizeof(WarpSlot<NCH, V, CAP>) + bank_bytes + 15) & ~(size_t)15;
+    bool global_banks = false;
+    if ((int)(SMALL_SMEM_MAX_WARP / slot) < MAXW && bank_bytes > 4096) {
+        // banks to global memory: more warps per CTA matter more than the bank latency
+        global_banks = true;
+        slot = (sizeof(WarpSlot<NCH, V, CAP>) + 15) & ~(size_t)15;
+    }
     int nw = (int)(SMALL_SMEM_MAX_WARP / slot);
-    if (nw > 16) nw = 16;
+    if (nw > MAXW) nw = MAXW;
     if (nw < 1) SOAP_FAIL("soap_process_halos: a warp slot of %zu bytes does not fit in shared memory", slot);
-    auto kern = k_small_warps<NCH, V, CAP>;
+    auto kern = k_small_warps<NCH, V, CAP, MAXW>;
     const size_t smem = slot * nw;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned int grid = (unsigned int)h->sm_count;
     const unsigned int need = (n_upper + nw - 1) / nw;
     if (grid > need) grid = need < 1 ? 1 : need;
+    double* gbanks = nullptr;
+    if (global_banks) {
+        gbanks = (double*)h->get("h_tier_gbanks", bank_bytes * (size_t)grid * nw);
+        if (!gbanks) return -1;
+    }
     LAUNCH(h, kern, grid, 32 * nw, smem, stream, c->v, ha, cfg, list, n_list, overflow, n_overflow, queue_cursor, ctr,
-           bank_stride, (int)slot);
+           bank_stride, (int)slot, gbanks);
     return 0;
 }
 
@@ -753,7 +769,8 @@ int soap_small_tier_fits(const DevCfg& cfg, int tier) {
     else slot = full ? SLOT(8, V_FULL) : SLOT(8, V_MIN);
 #undef SLOT
     // at least four warps per CTA, or lock step buys nothing
-    return (slot + bank_bytes + 16) * 4 <= SMALL_SMEM_MAX_WARP ? 1 : 0;
+    (void)bank_bytes;  // large banks move to global memory (launch_warp_tier)
+    return (slot + 16) * 4 <= SMALL_SMEM_MAX_WARP ? 1 : 0;
 }
 
 int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int tier, const uint32_t* list,
