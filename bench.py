@@ -43,7 +43,7 @@ WORKLOADS = {
     "config2": (512**3, 200000, 284.4, 2.0e6),
     "config2_small": (128**3, 3125, 71.1, 2.0e5),  # same number densities, 1/64 of the volume
     # hydro variants (BASELINE config 3: gas/DM/stars/BH, exclusive+inclusive 30/50/100 kpc apertures + SO;
-    # "_kappa" adds kappa_corot, which runs on the general path only)
+    # "_kappa" adds kappa_corot, DtoT and the stellar rotation properties)
     "config3": (2 * 256**3, 50000, 142.2, 5.0e5),
     "config3_kappa": (2 * 256**3, 50000, 142.2, 5.0e5),
 }

@@ -945,7 +945,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     {
         long long prev = -1;
         for (int t = 0; t < NTIER; t++) {
-            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo) && dc.n_pj == 0 &&
+            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo && t == 2) && dc.n_pj == 0 &&
                          getenv("SOAP_B200_NO_TIERS") == nullptr;  // debugging / cross-check switch
             tl.lim[t] = tier_on[t] ? tier_nexp[t] : prev;  // a disabled tier takes no halos
             prev = tl.lim[t];

@@ -393,4 +393,170 @@ __device__ void write_row(const double* banks, const Cuts& cuts, int ncut, const
     }
 }
 
+// ------------------------------------------------------------ kappa_corot
+// get_angular_momentum_and_kappa_corot_weighted (kinematic_properties.py:266-425)
+// needs the direction of L before it can split the kinetic energy, so it runs
+// after k_moments has written L and vcom of every type: a second sweep adds up
+//   Kcorot = sum_{Li > 0, Ri2 != 0} 0.5 Li^2 / (m Ri2)   and   Mcounterrot = sum_{Li < 0} m
+// per selection (BoundSubhalo, apertures) and group (gas, stars, baryons) into the
+// kappa slots of the row; k_kappa_finish turns them into kappa_corot = Kcorot / K
+// and DtoT = 1 - 2 Mcounterrot / M (aperture_properties.py:1147-1270).
+struct KapSel {
+    double vc[3][3], lh[3][3];  // per group: reference velocity, unit angular momentum
+    int ok[3];
+    double ex[3], ey[3];  // in-plane axes of the stellar frame (cylindrical_coordinates.py:13-42)
+    int cyl_ok;           // Nstar >= 2 and sum(Lstar) != 0 (aperture_properties.py:1483-1490)
+    double R;
+    int incl, is_sub;
+    double* out;  // the block's 11 kappa / rotation slots
+};
+
+__device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl) {
+    const double* kin = blk + bl.kin;
+    const double Mg = blk[4], Ms = blk[6];
+    for (int g = 0; g < 3; g++) {
+        double L[3];
+        if (g < 2) {
+            const double* o = kin + 15 * (g == 0 ? 0 : 2);
+            for (int d = 0; d < 3; d++) { k.vc[g][d] = o[3 + d]; L[d] = o[6 + d]; }
+        } else {
+            for (int d = 0; d < 3; d++) {
+                L[d] = kin[45 + d];
+                k.vc[2][d] = (Mg + Ms) != 0.0 ? (Mg * kin[3 + d] + Ms * kin[30 + 3 + d]) / (Mg + Ms) : 0.0;
+            }
+        }
+        const double nrm = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+        k.ok[g] = nrm > 0.0;
+        for (int d = 0; d < 3; d++) k.lh[g][d] = nrm > 0.0 ? L[d] / nrm : 0.0;
+    }
+    k.out = blk + bl.kappa;
+    // stellar frame: z = L_star / |L_star|, x = helper x z normalised, y = z x x
+    {
+        const double* o = kin + 30;
+        const double Lx = o[6], Ly = o[7], Lz = o[8];
+        k.cyl_ok = blk[2] >= 2.0 && (Lx + Ly + Lz) != 0.0 && k.ok[1];
+        const double* z = k.lh[1];
+        // np.allclose(z_axis, [1, 0, 0], rtol=0.1): |z - h| <= 1e-8 + 0.1 |h| per component
+        const bool near_x = fabs(z[0] - 1.0) <= 1e-8 + 0.1 && fabs(z[1]) <= 1e-8 && fabs(z[2]) <= 1e-8;
+        const double hx = near_x ? 0.0 : 1.0, hy = near_x ? 1.0 : 0.0, hz = 0.0;
+        double x[3] = {hy * z[2] - hz * z[1], hz * z[0] - hx * z[2], hx * z[1] - hy * z[0]};
+        const double xn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        for (int d = 0; d < 3; d++) k.ex[d] = xn > 0.0 ? x[d] / xn : 0.0;
+        k.ey[0] = z[1] * k.ex[2] - z[2] * k.ex[1];
+        k.ey[1] = z[2] * k.ex[0] - z[0] * k.ex[2];
+        k.ey[2] = z[0] * k.ex[1] - z[1] * k.ex[0];
+        if (!(xn > 0.0)) k.cyl_ok = 0;  // the reference divides by zero here (L anti-parallel to x)
+    }
+}
+
+
+// the selections of halo h committed at this rung that carry kappa slots; returns their number
+__device__ inline int kappa_build_sels(KapSel* sel, const DevCfg& cfg, const HaloArrays& ha, uint32_t h, int c_lo,
+                                       int c_hi) {
+    const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
+    double* row = ha.out + (int64_t)h * ha.ncol;
+    int n = 0;
+    if (cfg.do_sub && c_lo == 0) {
+        kappa_refs(sel[n], row + cfg.lay.sub, cfg.lay.bsub);
+        sel[n].is_sub = 1; sel[n].incl = 0; sel[n].R = 0.0;
+        n++;
+    }
+    for (int a = 0; a < cfg.n_ap; a++)
+        if (off_ap + a >= c_lo && off_ap + a < c_hi) {
+            kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap);
+            sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a];
+            n++;
+        }
+    return n;
+}
+
+// one gas or star particle (halo-centred x, y, z, r) into the raw sums acc[selection][11]
+__device__ __forceinline__ void kappa_add(const KapSel* sel, int ns, double (*acc)[11], double x, double y, double z,
+                                          double r, double m, double vx, double vy, double vz, uint32_t tc,
+                                          bool bound) {
+    const double rr2 = x * x + y * y + z * z;
+    const int g0 = tc == 0u ? 0 : 1;
+    for (int s = 0; s < ns; s++) {
+        const KapSel& k = sel[s];
+        const bool in = k.is_sub ? bound : (r <= k.R && (k.incl || bound));
+        if (!in) continue;
+        for (int gi = 0; gi < 2; gi++) {
+            const int g = gi == 0 ? g0 : 2;
+            if (!k.ok[g]) continue;
+            const double ux = vx - k.vc[g][0], uy = vy - k.vc[g][1], uz = vz - k.vc[g][2];
+            const double lx = m * (y * uz - z * uy), ly = m * (z * ux - x * uz), lz = m * (x * uy - y * ux);
+            const double Li = lx * k.lh[g][0] + ly * k.lh[g][1] + lz * k.lh[g][2];
+            const double rdl = x * k.lh[g][0] + y * k.lh[g][1] + z * k.lh[g][2];
+            const double Ri2 = rr2 - rdl * rdl;
+            if (Ri2 != 0.0 && Li > 0.0) atomicAdd(&acc[s][g], 0.5 * (Li * Li / (m * Ri2)));
+            if (g < 2 && Li < 0.0) atomicAdd(&acc[s][3 + g], m);
+        }
+        if (tc == 2u && k.cyl_ok) {
+            // cylindrical velocity of a star in the frame of L_star, about vcom_star
+            // (calculate_cylindrical_velocities, cylindrical_coordinates.py:45-93)
+            const double ux = vx - k.vc[1][0], uy = vy - k.vc[1][1], uz = vz - k.vc[1][2];
+            const double X = x * k.ex[0] + y * k.ex[1] + z * k.ex[2];
+            const double Y = x * k.ey[0] + y * k.ey[1] + z * k.ey[2];
+            const double VX = ux * k.ex[0] + uy * k.ex[1] + uz * k.ex[2];
+            const double VY = ux * k.ey[0] + uy * k.ey[1] + uz * k.ey[2];
+            const double VZ = ux * k.lh[1][0] + uy * k.lh[1][1] + uz * k.lh[1][2];
+            const double Rp = sqrt(X * X + Y * Y);
+            const double cph = Rp > 0.0 ? X / Rp : 1.0, sph = Rp > 0.0 ? Y / Rp : 0.0;  // arctan2(0, 0) = 0
+            const double vr = VX * cph + VY * sph, vp = -VX * sph + VY * cph;
+            atomicAdd(&acc[s][5], m * vr); atomicAdd(&acc[s][6], m * vp); atomicAdd(&acc[s][7], m * VZ);
+            atomicAdd(&acc[s][8], m * vr * vr); atomicAdd(&acc[s][9], m * vp * vp); atomicAdd(&acc[s][10], m * VZ * VZ);
+        }
+    }
+}
+
+// raw sums -> kappa_corot / DtoT / stellar rotation, once per selection, at the rung that committed it
+__device__ inline void kappa_finish_row(const DevCfg& cfg, const HaloArrays& ha, uint32_t h, int c_lo, int c_hi) {
+    const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
+    double* row = ha.out + (int64_t)h * ha.ncol;
+    auto fin = [&](double* blk, const BlockLayout& bl) {
+        const double* kin = blk + bl.kin;
+        double* o = blk + bl.kappa;
+        const double Mg = blk[4], Ms = blk[6];
+        const double* gk = kin;        // gas: com 3, vcom 3, L 3, veldisp 6
+        const double* sk = kin + 30;   // stars
+        const double trg = gk[9] + gk[10] + gk[11], trs = sk[9] + sk[10] + sk[11];
+        const double Kg = 0.5 * Mg * trg, Ks = 0.5 * Ms * trs;
+        double Kb = 0.0;
+        if (Mg + Ms != 0.0) {
+            double dg = 0.0, ds = 0.0;
+            for (int d = 0; d < 3; d++) {
+                const double vb = (Mg * gk[3 + d] + Ms * sk[3 + d]) / (Mg + Ms);
+                dg += (gk[3 + d] - vb) * (gk[3 + d] - vb);
+                ds += (sk[3 + d] - vb) * (sk[3 + d] - vb);
+            }
+            Kb = 0.5 * (Mg * (trg + dg) + Ms * (trs + ds));
+        }
+        const double kc_g = o[0], kc_s = o[1], kc_b = o[2], mc_g = o[3], mc_s = o[4];
+        o[0] = Kg > 0.0 ? kc_g / Kg : 0.0;
+        o[1] = Ks > 0.0 ? kc_s / Ks : 0.0;
+        o[2] = Kb > 0.0 ? kc_b / Kb : 0.0;
+        o[3] = Mg != 0.0 ? 1.0 - 2.0 * mc_g / Mg : 0.0;
+        o[4] = Ms != 0.0 ? 1.0 - 2.0 * mc_s / Ms : 0.0;
+        // stellar rotation and cylindrical dispersions (kinematic_properties.py:17-51,130-178;
+        // aperture_properties.py:1502-1536): mean v_phi, sqrt(sum sigma^2 / 3), sigma_z, sqrt(sigma_r^2 + sigma_phi^2)
+        {
+            double mean[3], var[3];
+            const bool have = Ms != 0.0 && (o[5] != 0.0 || o[6] != 0.0 || o[7] != 0.0 || o[8] != 0.0 || o[9] != 0.0 || o[10] != 0.0);
+            for (int c = 0; c < 3; c++) {
+                mean[c] = have ? o[5 + c] / Ms : 0.0;
+                var[c] = have ? fmax(o[8 + c] / Ms - mean[c] * mean[c], 0.0) : 0.0;
+            }
+            o[5] = mean[1];
+            o[6] = sqrt((var[0] + var[1] + var[2]) / 3.0);
+            o[7] = sqrt(var[2]);
+            o[8] = sqrt(var[0] + var[1]);
+            o[9] = 0.0;
+            o[10] = 0.0;
+        }
+    };
+    if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
+    for (int a = 0; a < cfg.n_ap; a++)
+        if (off_ap + a >= c_lo && off_ap + a < c_hi) fin(row + cfg.lay.ap[a], cfg.lay.bap);
+}
+
 #endif  // __CUDACC__

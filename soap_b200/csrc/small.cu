@@ -667,6 +667,40 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_small_warps(ChunkView v, HaloA
                 __syncwarp();
                 write_row<V, NTY>(banks, W.cuts, ncut, cfg, ha, h, sr, sub_c, n_so, cx, cy, cz, lane);
                 __syncwarp();
+                if constexpr (NCH == 8 && V >= V_FULL) if (cfg.flags & PF_KAPPA) {
+                    // kappa_corot / DtoT / stellar rotation need the finished vcom and L of the row:
+                    // a second pass over the gas and star records (scratch aliases the staging tile)
+                    constexpr int KS = 1 + SOAP_MAX_APERTURES;
+                    static_assert(sizeof(W.stage) >= KS * (sizeof(KapSel) + 11 * sizeof(double)), "kappa scratch");
+                    KapSel* ksel = reinterpret_cast<KapSel*>(W.stage);
+                    double(*kacc)[11] = reinterpret_cast<double(*)[11]>(ksel + KS);
+                    int ns = 0;
+                    if (lane == 0) ns = kappa_build_sels(ksel, cfg, ha, h, c_lo, c_hi);
+                    ns = __shfl_sync(0xffffffffu, ns, 0);
+                    if (ns > 0) {
+                        for (int i = lane; i < ns * 11; i += 32) (&kacc[0][0])[i] = 0.0;
+                        __syncwarp();
+                        for (uint32_t i = lane; i < n; i += 32) {
+                            const Rec rc = W.rec[i];
+                            const uint32_t tc = rc.flags & 3u;
+                            if (tc != 0u && tc != 2u) continue;
+                            const uint32_t t = W.pid[i];
+                            const double x = rewrap_rel(v.px[t], cx, L, halfL);
+                            const double y = rewrap_rel(v.py[t], cy, L, halfL);
+                            const double z = rewrap_rel(v.pz[t], cz, L, halfL);
+                            kappa_add(ksel, ns, kacc, x, y, z, radius3(x, y, z), (double)v.mass[t], (double)v.vx[t],
+                                      (double)v.vy[t], (double)v.vz[t], tc, (rc.flags & 4u) != 0u);
+                        }
+                        __syncwarp();
+                        for (int i = lane; i < ns * 11; i += 32) {
+                            const double a = kacc[i / 11][i % 11];
+                            if (a != 0.0) ksel[i / 11].out[i % 11] += a;
+                        }
+                        __syncwarp();
+                        if (lane == 0) kappa_finish_row(cfg, ha, h, c_lo, c_hi);
+                        __syncwarp();
+                    }
+                }
             }
             int st = 0;
             if (lane == 0) st = ha.state[h];
