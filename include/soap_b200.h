@@ -136,7 +136,8 @@ typedef struct {
     double proj_physical_mpc[SOAP_MAX_APERTURES];
     /* property groups: bit 0 kinematics (veldisp, L), bit 1 kappa_corot / DtoT and the stellar
      * rotational velocity / cylindrical dispersions (needs bit 0), bit 2 non-iterative inertia
-     * tensors, bit 3 half-mass radii per type (also the projected ones) */
+     * tensors, bit 3 half-mass radii per type (also the projected ones), bit 4 the iterative
+     * 3-D inertia tensors (inertia_tensors.py:19-132, max_iterations = 20; needs bit 2) */
     uint32_t property_flags;
     int dmo;                  /* only dark matter present / requested */
 } soap_halo_config;

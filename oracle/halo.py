@@ -68,6 +68,8 @@ class Params:
     critical_density: float = 1.0
     mean_density: float = 1.0
     faithful: bool = True
+    # also the iterative tensors (inertia_tensors.py default max_iterations = 20)
+    iterative_tensors: bool = False
 
 
 def _cast(arr, faithful):
@@ -144,14 +146,14 @@ def _store_group(res, prefix, blk, with_kappa):
         res[f"DtoT{prefix}"] = blk["DtoT"]
 
 
-def _tensor(mass, pos, R, params, reduced, search_radius=None):
+def _tensor(mass, pos, R, params, reduced, search_radius=None, max_iterations=1):
     t = get_weighted_inertia_tensor(
         mass,
         pos,
         R,
         search_radius=search_radius,
         reduced=reduced,
-        max_iterations=1,
+        max_iterations=max_iterations,
         kpc_per_length=params.kpc_per_length,
     )
     return t
@@ -272,6 +274,9 @@ class SOOracle:
                 m2 = dm_m[outside][i]
                 dm_missed_mass = m2 * (SO_r - r1) / (r2 - r1)
         sel = radius < SO_r  # SO_properties.py:485
+        # in-sphere + "surrounding" particles (SO_properties.py:490-496,629-630)
+        mass_all = np.concatenate([mass[sel], mass[~sel]])
+        position_all = np.concatenate([position[sel], position[~sel]])
         mass = mass[sel]
         radius = radius[sel]
         position = position[sel]
@@ -305,6 +310,12 @@ class SOOracle:
                 if t is not None:
                     nm = "TotalInertiaTensor" + ("Reduced" if reduced else "")
                     res[nm + "Noniterative"] = t
+            if p.iterative_tensors:  # SO_properties.py:621-648
+                for reduced in (False, True):
+                    t = _tensor(mass_all, position_all, SO_r, p, reduced, search_radius=search_radius,
+                                max_iterations=20)
+                    if t is not None:
+                        res["TotalInertiaTensor" + ("Reduced" if reduced else "")] = t
         res["Mfrac_satellites"] = mass[is_sat].sum() / SO_mass
         res["Mfrac_external"] = mass[is_ext].sum() / SO_mass
         for t, nm, kap in ((0, "gas", True), (1, "dm", False), (4, "star", True)):
@@ -460,6 +471,10 @@ class SubhaloOracle:
             t = _tensor(mass, position, 10 * res["HalfMassRadiusTot"], p, reduced)
             if t is not None:
                 res["TotalInertiaTensor" + ("Reduced" if reduced else "") + "Noniterative"] = t
+            if p.iterative_tensors:  # subhalo_properties.py:1075-1100
+                t = _tensor(mass, position, 10 * res["HalfMassRadiusTot"], p, reduced, max_iterations=20)
+                if t is not None:
+                    res["TotalInertiaTensor" + ("Reduced" if reduced else "")] = t
 
 
 # -------------------------------------------------------------------- apertures
@@ -552,6 +567,10 @@ class ApertureOracle:
             t = _tensor(star_mass_all, star_pos_all, self.aperture_radius, p, reduced)
             if t is not None:
                 res["StellarInertiaTensor" + ("Reduced" if reduced else "") + "Noniterative"] = t
+            if p.iterative_tensors:  # aperture_properties.py:3613-3636
+                t = _tensor(star_mass_all, star_pos_all, self.aperture_radius, p, reduced, max_iterations=20)
+                if t is not None:
+                    res["StellarInertiaTensor" + ("Reduced" if reduced else "")] = t
 
 
 class ProjectedApertureOracle:

@@ -31,6 +31,12 @@ int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, co
 int soap_launch_projected(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
                           const unsigned int* n_items_dev, unsigned int n_items_host, unsigned int n_mslot,
                           unsigned int grid, cudaStream_t stream);
+int soap_iter_list(soap_handle* h, const HaloArrays& ha, int64_t nh, uint32_t* list, unsigned int* n_list_dev,
+                   unsigned int* n_host, cudaStream_t stream);
+int soap_launch_iter_tensors(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int64_t nh, const Item* items,
+                             const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* list,
+                             const unsigned int* n_list_dev, unsigned int n_list_host, unsigned int grid,
+                             cudaStream_t stream);
 int soap_small_tier_fits(const DevCfg& cfg, int tier);
 int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int tier, const uint32_t* list,
                       const unsigned int* n_list, unsigned int n_list_upper, uint32_t* overflow,
@@ -780,6 +786,8 @@ int validate_cfg(const soap_halo_config* cfg) {
         SOAP_FAIL("config: n_projected=%d outside [0,%d]", cfg->n_projected, SOAP_MAX_APERTURES);
     for (int a = 1; a < cfg->n_projected; a++)
         if (cfg->proj_radius[a] < cfg->proj_radius[a - 1]) SOAP_FAIL("config: projected aperture radii must ascend");
+    if ((cfg->property_flags & PF_ITER) && !(cfg->property_flags & PF_TENS))
+        SOAP_FAIL("config: iterative inertia tensors (property_flags bit 4) need the tensor group (bit 2)");
     if (cfg->n_projected > 0 && !cfg->do_subhalo)
         SOAP_FAIL("config: projected apertures need BoundSubhalo first (they assume every bound particle is loaded)");
     if (!(cfg->boxsize > 0.0)) SOAP_FAIL("config: boxsize must be positive");
@@ -822,6 +830,10 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
         if (cfg->property_flags & PF_TENS) {
             add(p + (kind == 2 ? "StellarInertiaTensorNoniterative" : "TotalInertiaTensorNoniterative"), 6);
             add(p + (kind == 2 ? "StellarInertiaTensorReducedNoniterative" : "TotalInertiaTensorReducedNoniterative"), 6);
+            if (cfg->property_flags & PF_ITER) {
+                add(p + (kind == 2 ? "StellarInertiaTensor" : "TotalInertiaTensor"), 6);
+                add(p + (kind == 2 ? "StellarInertiaTensorReduced" : "TotalInertiaTensorReduced"), 6);
+            }
         }
         if (cfg->property_flags & PF_HMR) {
             add(p + "HalfMassRadiusGas", 1); add(p + "HalfMassRadiusDM", 1); add(p + "HalfMassRadiusStar", 1);
@@ -997,36 +1009,36 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     if (trace)
         fprintf(stderr, "[soap_b200] tiers: lists %u %u %u -> general %u | small pairs %llu %llu %llu\n", 0u, 0u, 0u, n_pend,
                 (unsigned long long)small_ctr[0].pairs, (unsigned long long)small_ctr[1].pairs, (unsigned long long)small_ctr[2].pairs);
+    // plan a sweep per halo of `list`; coarse meshes / huge spheres can need more
+    // work items than provisioned: grow the list and plan again
+    auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int look, int replan) -> int {
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 3 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow
+            LAUNCH(h, k_plan_items, grid_for(n_host, 128), 128, 0, stream, v, ha, list, n_dev, items,
+                   (unsigned int)items_cap, ctr, look, replan);
+            Counters pc;
+            CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (!pc.items_overflow) return 0;
+            if (attempt == 1 || pc.n_items >= 0xfff00000u)
+                SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", pc.n_items);
+            items_cap = (size_t)pc.n_items + 1024;
+            items = (Item*)h->get("h_items", sizeof(Item) * items_cap);
+            item_minr = (unsigned long long*)h->get("h_item_minr", sizeof(unsigned long long) * items_cap);
+            item_minfof = (int32_t*)h->get("h_item_minfof", sizeof(int32_t) * items_cap);
+            if (!items || !item_minr || !item_minfof) return -1;
+            if (!replan) CUDA_TRY(cudaMemsetAsync(&ctr->candidates, 0, sizeof(unsigned long long), stream));
+        }
+        return 0;
+    };
     while (n_pend > 0) {
         c->last_rounds++;
         if (c->last_rounds > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
         CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), stream));
         // ladder look-ahead: the first round covers 4 rungs per sweep, stragglers more
         const int look = c->last_rounds == 1 ? 4 : LOOK_MAX;
-        // plan a sweep per halo of `list`; coarse meshes / huge spheres can need more
-        // work items than provisioned: grow the list and plan again
-        auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int replan) -> int {
-            for (int attempt = 0; attempt < 2; attempt++) {
-                CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 3 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow
-                LAUNCH(h, k_plan_items, grid_for(n_host, 128), 128, 0, stream, v, ha, list, n_dev, items,
-                       (unsigned int)items_cap, ctr, look, replan);
-                Counters pc;
-                CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                CUDA_TRY(cudaStreamSynchronize(stream));
-                if (!pc.items_overflow) return 0;
-                if (attempt == 1 || pc.n_items >= 0xfff00000u)
-                    SOAP_FAIL("soap_process_halos: work item list overflow (%u items)", pc.n_items);
-                items_cap = (size_t)pc.n_items + 1024;
-                items = (Item*)h->get("h_items", sizeof(Item) * items_cap);
-                item_minr = (unsigned long long*)h->get("h_item_minr", sizeof(unsigned long long) * items_cap);
-                item_minfof = (int32_t*)h->get("h_item_minfof", sizeof(int32_t) * items_cap);
-                if (!items || !item_minr || !item_minfof) return -1;
-                if (!replan) CUDA_TRY(cudaMemsetAsync(&ctr->candidates, 0, sizeof(unsigned long long), stream));
-            }
-            return 0;
-        };
         log.begin("plan", stream);
-        if (plan(pend, n_pend_dev, n_pend, 0)) return -1;
+        if (plan(pend, n_pend_dev, n_pend, look, 0)) return -1;
         log.end(stream);
         log.begin("count", stream);
         LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr);
@@ -1045,7 +1057,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             const unsigned int n_try = hc.n_try + hc.n_big;
             // the accepted radius is generally smaller than the swept one: plan its sweep
             log.begin("plan", stream);
-            if (plan(acc_list, &ctr->n_acc, n_try, 1)) return -1;
+            if (plan(acc_list, &ctr->n_acc, n_try, look, 1)) return -1;
             log.end(stream);
             CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1180,6 +1192,22 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                     (unsigned long long)hc.rec_total, (unsigned long long)hc2.pairs, hc2.n_next);
         n_pend = hc2.n_next;
         uint32_t* t = pend; pend = next; next = t;
+    }
+    if (dc.flags & PF_ITER) {
+        // iterative inertia tensors: repeated sweeps of the finished halos (iter.cu)
+        log.begin("iter_tensors", stream);
+        unsigned int n_fin = 0;
+        if (soap_iter_list(h, ha, (int64_t)H, acc_list, &ctr->n_acc, &n_fin, stream)) return -1;
+        if (n_fin > 0) {
+            if (plan(acc_list, &ctr->n_acc, n_fin, 1, 1)) return -1;
+            Counters pc;
+            CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (soap_launch_iter_tensors(c, dc, ha, (int64_t)H, items, &ctr->n_items, pc.n_items, acc_list, &ctr->n_acc,
+                                         n_fin, sweep_grid, stream))
+                return -1;
+        }
+        log.end(stream);
     }
     if (soap_write_input_cols(h, ha, (int64_t)H, stream)) return -1;
     CUDA_TRY(cudaStreamSynchronize(stream));

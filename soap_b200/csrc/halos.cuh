@@ -5,7 +5,7 @@
 constexpr double SOAP_PI = 3.141592653589793;
 
 // property_flags bits (include/soap_b200.h)
-constexpr uint32_t PF_KIN = 1u, PF_KAPPA = 2u, PF_TENS = 4u, PF_HMR = 8u;
+constexpr uint32_t PF_KIN = 1u, PF_KAPPA = 2u, PF_TENS = 4u, PF_HMR = 8u, PF_ITER = 16u;
 
 // One in-sphere particle of one halo, the unit of the segmented radial sort.
 struct __align__(16) Rec {
@@ -45,7 +45,7 @@ __host__ __device__ inline BlockLayout block_layout(uint32_t flags, int n_extra)
     b.kappa = (flags & PF_KAPPA) ? o : -1;
     if (flags & PF_KAPPA) o += 11;  // kappa x3, DtoT x2, stellar rotation + cylindrical dispersions x4, 2 scratch
     b.tens = (flags & PF_TENS) ? o : -1;
-    if (flags & PF_TENS) o += 12;
+    if (flags & PF_TENS) o += (flags & PF_ITER) ? 24 : 12;  // non-iterative pair, then the iterative pair
     b.hmr = (flags & PF_HMR) ? o : -1;
     if (flags & PF_HMR) o += 4;
     b.extra = o;

@@ -292,6 +292,7 @@ __device__ void write_row(const double* banks, const Cuts& cuts, int ncut, const
                 for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, ncut, true, 1u << t, S[t]);
                 double* blk = row + L.sub;
                 write_block<V>(blk, L.bsub, S, centre, cfg, cfg.flags);
+                if ((cfg.flags & PF_ITER) && L.bsub.tens >= 0) blk[L.bsub.tens + 12] = ha.rung_r[h];  // iter.cu
                 const double Mtot = blk[8];
                 blk[15] = Mtot != 0.0 ? sqrt(sr->sub_vmax_s_v * cfg.G) : 0.0;
                 blk[16] = Mtot != 0.0 ? sr->sub_vmax_s_r : 0.0;
@@ -327,6 +328,7 @@ __device__ void write_row(const double* banks, const Cuts& cuts, int ncut, const
                 for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, pos, false, 1u << t, S[t]);
                 double* blk = row + L.so[q];
                 write_block<V>(blk, L.bso, S, centre, cfg, cfg.flags);
+                if ((cfg.flags & PF_ITER) && L.bso.tens >= 0) blk[L.bso.tens + 12] = ha.rung_r[h];  // iter.cu
                 const double Mpart = blk[8];
                 const double SO_r = sr->so_r[q], SO_m = sr->so_mass[q];
                 const double vmax = Mpart != 0.0 ? sqrt(sr->so_vmax_v[q] * cfg.G) : 0.0;
@@ -380,6 +382,7 @@ __device__ void write_row(const double* banks, const Cuts& cuts, int ncut, const
                 for (int t = 0; t < 4; t++) sel_sum<V>(banks, NTY, pos, excl, 1u << t, S[t]);
                 double* blk = row + L.ap[a];
                 write_block<V>(blk, L.bap, S, centre, cfg, cfg.flags);
+                if ((cfg.flags & PF_ITER) && L.bap.tens >= 0) blk[L.bap.tens + 12] = ha.rung_r[h];  // iter.cu
                 if (cfg.flags & PF_HMR)
                     for (int g = 0; g < 4; g++) blk[L.bap.hmr + g] = sr->ap_hmr[a][g];
                 if ((cfg.flags & PF_TENS) && S[2][V_M] != 0.0) {

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 
-PF_KIN, PF_KAPPA, PF_TENS, PF_HMR = 1, 2, 4, 8
+PF_KIN, PF_KAPPA, PF_TENS, PF_HMR, PF_ITER = 1, 2, 4, 8, 16
 
 SEARCH_RADIUS_FACTOR = 1.2  # halo_tasks.py:14
 READ_RADIUS_FACTOR = 1.5  # halo_tasks.py:17

@@ -50,9 +50,10 @@ def oracle_prop_list(params, cp, so, apertures, do_subhalo=True, projected=()):
     return props
 
 
-def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True, projected=()):
+def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True, projected=(), iterative=False):
     """Returns list (per halo) of (halo_result or None, info, input_halo)."""
     params = oracle_params(cp, faithful)
+    params.iterative_tensors = bool(iterative)
     meshes = {t: om.MeshOracle(d["Coordinates"], om.mesh_resolution(len(d["Masses"]))) for t, d in data.items()}
     props = oracle_prop_list(params, cp, so, apertures, do_subhalo, projected)
     td = oh.target_density_of(props, params)
@@ -230,7 +231,9 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
                     rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_SECOND, scale=300.0)
             if flags & 4:
                 tn = "StellarInertiaTensor" if kind == "ap" else "TotalInertiaTensor"
-                for suffix in ("Noniterative", "ReducedNoniterative"):
+                # iterative variants (flags bit 4): same tolerance; a particle exactly on the
+                # ellipsoid surface could flip a pass, which none of the seeded cases hits
+                for suffix in ("Noniterative", "ReducedNoniterative") + (("", "Reduced") if flags & 16 else ()):
                     k = tn + suffix
                     ref = np.asarray(o.get(k, np.zeros(6)), dtype=np.float64)
                     rep.check(pre + k, h, g(k), ref, TOL_SECOND,

@@ -17,7 +17,8 @@ def _run(data, H, cp, so, apertures, flags, dmo, fine_ppc=0, halos=None, project
     cfg = cmp.device_config(cp, so=so, apertures=apertures, flags=flags, dmo=dmo, projected=projected)
     chunk = DeviceChunk(data, cp["boxsize"], fine_ppc=fine_ppc)
     res = process_halos(chunk, cfg, H)
-    oracle_out, props = cmp.run_oracle(data, H, cp, so, apertures, faithful=False, halos=halos, projected=projected)
+    oracle_out, props = cmp.run_oracle(data, H, cp, so, apertures, faithful=False, halos=halos, projected=projected,
+                                       iterative=bool(flags & 16))
     rep = cmp.compare(res, oracle_out, props, cp, halos=halos, flags=flags)
     print("max errors:", {k: float(f"{v:.3g}") for k, v in sorted(rep.maxerr.items())})
     print("timings:", chunk.timings())
@@ -65,6 +66,29 @@ def test_dummy_chunk_kappa_corot_and_disc_fractions():
                                 npart_choices=(1, 10, 100, 1000, 5000))
     aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 100.0) for incl in (0, 1)]
     _run(data, H, cp, SO4[:1], aps, flags=1 | 2, dmo=False)
+
+
+def test_iterative_inertia_tensors_hydro():
+    """Total/StellarInertiaTensor[Reduced] with the reference's default 20 re-selection passes
+    (inertia_tensors.py:19-132) for BoundSubhalo, SO (in-sphere + surrounding particles) and
+    exclusive / inclusive apertures"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(977, 30, boxsize=L, n_background=50000,
+                                npart_choices=(10, 100, 1000, 5000))
+    aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 100.0) for incl in (0, 1)]
+    res, rep = _run(data, H, cp, SO4[:2], aps, flags=1 | 4 | 8 | 16, dmo=False)
+    t = res.get("BoundSubhalo/TotalInertiaTensor")
+    assert (np.abs(t).sum(axis=1) > 0).sum() >= 10  # the iterative tensors were really computed
+
+
+def test_iterative_inertia_tensors_dmo():
+    L = 40.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.to_numpy(*synth.nfw_chunk(300000, 200, L, seed=5, max_np=20000))
+    res, rep = _run(data, H, cp, SO4[:2], [], flags=4 | 16, dmo=True)
+    t = res.get("SO/0/TotalInertiaTensorReduced")
+    assert (np.abs(t).sum(axis=1) > 0).sum() >= 50
 
 
 def test_dummy_chunk_projected_apertures():
