@@ -641,6 +641,13 @@ class ProjectedApertureOracle:
                 )
                 if t is not None:
                     res["ProjectedTotalInertiaTensor" + ("Reduced" if reduced else "") + "Noniterative"] = t
+                if p.iterative_tensors:  # projected_aperture_properties.py:789-852
+                    t = get_weighted_projected_inertia_tensor(
+                        mass, position, iproj, self.aperture_radius, reduced=reduced,
+                        max_iterations=20, kpc_per_length=p.kpc_per_length,
+                    )
+                    if t is not None:
+                        res["ProjectedTotalInertiaTensor" + ("Reduced" if reduced else "")] = t
 
 
 # -------------------------------------------------------------------- halo loop

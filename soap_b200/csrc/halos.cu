@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) k_pj_scan(HaloArrays ha, DevCfg cfg, cons
             const int p = threadIdx.x / NG, g = threadIdx.x % NG;
             // half the mass of type g inside aperture p of this projection (written by k_projected);
             // block columns 4.. are the masses of type codes gas, dm, star, bh
-            thr[p][g] = 0.5 * row[cfg.lay.pj[p] + ax * PJ_BLOCK + 4 + g];
+            thr[p][g] = 0.5 * row[cfg.lay.pj[p] + ax * cfg.lay.pjb + 4 + g];
             cap_i[p][g] = 0xffffffffu;
         }
         if (threadIdx.x < NG) carry[threadIdx.x] = 0.0;
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256) k_pj_scan(HaloArrays ha, DevCfg cfg, cons
                 if (Wmin == Wmax) hm = 0.5 * (rmin_ + rmax_);
                 else hm = rmin_ + (thr[p][g] - Wmin) / (Wmax - Wmin) * (rmax_ - rmin_);
             }
-            row[cfg.lay.pj[p] + ax * PJ_BLOCK + 18 + g] = hm;
+            row[cfg.lay.pj[p] + ax * cfg.lay.pjb + 18 + g] = hm;
         }
         __syncthreads();
     }
@@ -861,6 +861,10 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
             add(p + "HalfMassRadiusGas", 1); add(p + "HalfMassRadiusDm", 1); add(p + "HalfMassRadiusStar", 1);
             add(p + "ProjectedTotalInertiaTensorNoniterative", 3);
             add(p + "ProjectedTotalInertiaTensorReducedNoniterative", 3);
+            if (cfg->property_flags & PF_ITER) {
+                add(p + "ProjectedTotalInertiaTensor", 3);
+                add(p + "ProjectedTotalInertiaTensorReduced", 3);
+            }
         }
     if (buf && buflen > 0) {
         if ((int64_t)s.size() + 1 > buflen) { snprintf(g_soap_err, sizeof(g_soap_err), "soap_result_layout: buffer too small (%zu needed)", s.size() + 1); return -1; }

@@ -67,6 +67,7 @@ struct RowLayout {
     int so[SOAP_MAX_SO];
     int ap[SOAP_MAX_APERTURES];
     int pj[SOAP_MAX_APERTURES];
+    int pjb;  // columns of one projection block: PJ_BLOCK (+ the iterative tensor pair)
     BlockLayout bsub, bso, bap;
 };
 
@@ -75,6 +76,7 @@ inline RowLayout row_layout(const soap_halo_config& cfg) {
     L.bsub = block_layout(cfg.property_flags, N_SUB_EXTRA);
     L.bso = block_layout(cfg.property_flags, N_SO_EXTRA);
     L.bap = block_layout(cfg.property_flags, 0);
+    L.pjb = PJ_BLOCK + ((cfg.property_flags & PF_ITER) ? 6 : 0);
     int o = N_INPUT_COLS;
     L.sub = -1;
     if (cfg.do_subhalo) { L.sub = o; o += L.bsub.size; }
@@ -88,7 +90,7 @@ inline RowLayout row_layout(const soap_halo_config& cfg) {
     }
     for (int a = 0; a < SOAP_MAX_APERTURES; a++) {
         L.pj[a] = -1;
-        if (a < cfg.n_projected) { L.pj[a] = o; o += 3 * PJ_BLOCK; }
+        if (a < cfg.n_projected) { L.pj[a] = o; o += 3 * L.pjb; }
     }
     L.ncol = o;
     return L;

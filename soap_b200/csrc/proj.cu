@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TB) k_projected(ChunkView v, HaloArrays ha, De
         // ------------------------------------------------- rows: one thread per (radius, axis)
         if ((int)threadIdx.x < npj * 3) {
             const int p = threadIdx.x / 3, ax = threadIdx.x % 3;
-            double* blk = ha.out + (int64_t)h * ha.ncol + cfg.lay.pj[p] + ax * PJ_BLOCK;
+            double* blk = ha.out + (int64_t)h * ha.ncol + cfg.lay.pj[p] + ax * cfg.lay.pjb;
             double S[4][PV], T[PV];
             double n_all = 0.0;
             for (int t = 0; t < 4; t++)

@@ -162,7 +162,7 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
                     if flags & 8:
                         k = f"HalfMassRadius{nm.capitalize()}"
                         rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_MASS_RADIUS)
-                for suffix in ("Noniterative", "ReducedNoniterative"):
+                for suffix in ("Noniterative", "ReducedNoniterative") + (("", "Reduced") if flags & 16 else ()):
                     k = "ProjectedTotalInertiaTensor" + suffix
                     ref = np.asarray(o.get(k, np.zeros(3)), dtype=np.float64)
                     rep.check(pre + k, h, g(k), ref, TOL_SECOND, scale=(np.sqrt((ref[:2] ** 2).sum() + 2 * ref[2] ** 2) or None))

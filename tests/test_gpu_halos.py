@@ -82,6 +82,19 @@ def test_iterative_inertia_tensors_hydro():
     assert (np.abs(t).sum(axis=1) > 0).sum() >= 10  # the iterative tensors were really computed
 
 
+def test_iterative_projected_inertia_tensors():
+    """ProjectedTotalInertiaTensor[Reduced] (inertia_tensors.py:226-343, 20 passes) per axis"""
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(431, 30, boxsize=L, n_background=50000,
+                                npart_choices=(10, 100, 1000, 5000))
+    pj = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3) for kpc in (30.0, 100.0)]
+    aps = [(0.05 * cp["phys_mpc_to_coord"], 0.05, 0)]
+    res, rep = _run(data, H, cp, SO4[:1], aps, flags=4 | 8 | 16, dmo=False, projected=pj)
+    t = res.get("ProjectedAperture/1/projz/ProjectedTotalInertiaTensor")
+    assert (np.abs(t).sum(axis=1) > 0).sum() >= 10
+
+
 def test_iterative_inertia_tensors_dmo():
     L = 40.0
     cp = synth.coordinate_unit_params(L)
