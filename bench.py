@@ -46,6 +46,7 @@ WORKLOADS = {
     # "_kappa" adds kappa_corot, DtoT and the stellar rotation properties)
     "config3": (2 * 256**3, 50000, 142.2, 5.0e5),
     "config3_kappa": (2 * 256**3, 50000, 142.2, 5.0e5),
+    "config3_iter": (2 * 256**3, 50000, 142.2, 5.0e5),  # + the iterative inertia tensors (20 passes)
 }
 HYDRO_TYPES = {0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001}
 SEED = 20261018
@@ -235,11 +236,12 @@ def size_sample_and_time(data_np, H_np, L, cp, so_list, cores, budget_s):
 
 
 def build_config(cp, so_list, workload="config2"):
-    from soap_b200.halo_tasks import HaloPropConfig, PF_HMR, PF_KAPPA, PF_KIN, PF_TENS
+    from soap_b200.halo_tasks import HaloPropConfig, PF_HMR, PF_ITER, PF_KAPPA, PF_KIN, PF_TENS
 
     if workload.startswith("config3"):
         aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 50.0, 100.0) for incl in (0, 1)]
-        flags = PF_KIN | PF_TENS | PF_HMR | (PF_KAPPA if workload.endswith("kappa") else 0)
+        flags = PF_KIN | PF_TENS | PF_HMR | (PF_KAPPA if workload.endswith("kappa") else 0) | \
+            (PF_ITER if workload.endswith("iter") else 0)
         return HaloPropConfig(
             boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
             mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},

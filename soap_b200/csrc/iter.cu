@@ -196,15 +196,19 @@ __global__ void __launch_bounds__(TB) k_it_accum(ChunkView v, HaloArrays ha, Dev
                     } else {
                         val[1] = wq * paa; val[2] = wq * pbb; val[3] = wq * pab; val[4] = val[5] = val[6] = 0.0;
                     }
-                    val[7] = inside ? 1.0 : 0.0;
-                    val[8] = member ? 1.0 : 0.0;
+                    // the two counts by ballot; the weighted sums by butterfly, skipped when no lane is inside
+                    const unsigned b_in = __ballot_sync(0xffffffffu, inside);
+                    const unsigned b_mem = __ballot_sync(0xffffffffu, member);
+                    double* ws = wsum + ((size_t)wid * nt + 2 * s + red) * IT_NV;
+                    if (lane == 0) { ws[7] += (double)__popc(b_in); ws[8] += (double)__popc(b_mem); }
+                    if (b_in == 0u) continue;
 #pragma unroll
-                    for (int k = 0; k < IT_NV; k++) {
-                        if (proj >= 0 && k >= 4 && k <= 6) continue;
+                    for (int k = 0; k < 7; k++) {
+                        if (proj >= 0 && k >= 4) continue;
                         double a = val[k];
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                        if (lane == 0) wsum[((size_t)wid * nt + 2 * s + red) * IT_NV + k] += a;
+                        if (lane == 0) ws[k] += a;
                     }
                 }
             }
