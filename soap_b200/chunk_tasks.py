@@ -147,11 +147,25 @@ def gather_tables(table, index, dst=0, group=None):
     return t, i
 
 
-def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, group=None):
+# columns of the result table the re-read loop looks at (soap_result_layout: InputHalos/status,
+# InputHalos/search_radius, InputHalos/read_radius)
+COL_STATUS, COL_SEARCH_RADIUS, COL_READ_RADIUS = 0, 4, 5
+STATUS_RADIUS_TOO_SMALL = 1
+
+
+def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, group=None, reread=False,
+               max_passes=20):
     """Process every chunk owned by this rank with ``compute(chunk_data,
     chunk_halos) -> torch [H_c, ncol]`` and gather the rows on rank 0, ordered by
     halo index.  ``data[ptype]`` are numpy arrays of the whole box here (a real
-    run reads only the chunk's cells from the snapshot)."""
+    run reads only the chunk's cells from the snapshot).
+
+    ``reread=True`` adds the repeat loop of ChunkTask.__call__
+    (SOAP/core/chunk_tasks.py:188-367): halos that come back with status 1 (the
+    search radius outgrew the region that was read, halo_tasks.py:386-402) are
+    processed again, on the same rank, from a region re-cut with the enlarged
+    read radius the device returned, starting from the search radius it had
+    reached; everything else keeps its row from the pass that finished it."""
     import torch
 
     halo_s, chunk_size = peano_decomposition(boxsize, halo, nr_chunks)
@@ -159,11 +173,31 @@ def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, gr
     tables, indices = [], []
     for c in mine:
         hc = chunk_halos(halo_s, chunk_size, c)
-        cd = {}
-        for pt, d in data.items():
-            m = ghost_mask(d["Coordinates"], hc["cofp"], hc["read_radius"], boxsize)
-            cd[pt] = {k: np.ascontiguousarray(v[m]) for k, v in d.items()}
-        t = compute(cd, hc)
+        table_c = None
+        sel = np.arange(len(hc["index"]))
+        for _ in range(max_passes):
+            cur = {k: np.ascontiguousarray(np.asarray(v)[sel]) for k, v in hc.items()}
+            cd = {}
+            for pt, d in data.items():
+                m = ghost_mask(d["Coordinates"], cur["cofp"], cur["read_radius"], boxsize)
+                cd[pt] = {k: np.ascontiguousarray(v[m]) for k, v in d.items()}
+            t = compute(cd, cur)
+            if table_c is None:
+                table_c = t.clone()
+            else:
+                table_c[torch.as_tensor(sel, device=t.device)] = t
+            if not reread:
+                break
+            again = (t[:, COL_STATUS] == STATUS_RADIUS_TOO_SMALL).cpu().numpy()
+            if not again.any():
+                break
+            tn = t.detach().cpu().numpy()
+            for k in ("search_radius", "read_radius"):
+                hc[k] = np.array(hc[k], dtype=np.float64, copy=True)
+            hc["search_radius"][sel[again]] = tn[again, COL_SEARCH_RADIUS]
+            hc["read_radius"][sel[again]] = tn[again, COL_READ_RADIUS]
+            sel = sel[again]
+        t = table_c
         tables.append(t)
         indices.append(torch.as_tensor(np.asarray(hc["index"], dtype=np.int64), device=t.device))
     if tables:

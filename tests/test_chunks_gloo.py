@@ -79,6 +79,41 @@ def test_single_process_chunks_equal_whole_box():
     assert np.array_equal(t.numpy(), _whole_box(data, halo)[order])
 
 
+def test_reread_loop_repeats_only_the_halos_whose_region_was_too_small():
+    """chunk_tasks.py:188-367 / halo_tasks.py:386-402: status 1 -> read radius x factor, restart from
+    the search radius that was reached; rows of finished halos are kept"""
+    data, halo = _box(seed=9, nh=40)
+    need = 1.0 + 5.0 * np.random.default_rng(3).random(40)  # radius each halo must reach
+    need_of = dict(zip(halo["index"].tolist(), need.tolist()))
+    calls = []
+
+    def compute(cd, hc):
+        n = len(hc["index"])
+        calls.append(n)
+        out = np.zeros((n, 8))
+        for i in range(n):
+            want = need_of[int(hc["index"][i])]
+            if want > hc["read_radius"][i]:  # ladder hit the edge of what was read
+                out[i, 0] = 1
+                out[i, 4] = max(hc["search_radius"][i], hc["read_radius"][i])
+                out[i, 5] = max(1.5 * hc["read_radius"][i], out[i, 4])
+            else:
+                idx = om.brute_force_query(cd[1]["Coordinates"], hc["cofp"][i], want, L)
+                out[i, 6:] = [len(idx), want]
+        return torch.as_tensor(out)
+
+    t, i = ct.run_chunks(data, halo, L, 3, compute, reread=True)
+    t = t.numpy()
+    assert (t[:, 0] == 0).all() and len(calls) > 3 and calls[-1] < calls[0]
+    order = np.argsort(halo["index"])
+    for row, h in zip(t, order):
+        ref = om.brute_force_query(data[1]["Coordinates"], halo["cofp"][h], need[h], L)
+        assert row[6] == len(ref) and row[7] == need[h]
+    # without the loop the same run leaves the unfinished halos flagged
+    t0, _ = ct.run_chunks(data, halo, L, 3, compute, reread=False)
+    assert (t0.numpy()[:, 0] == 1).sum() == (need > 3.0).sum()
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

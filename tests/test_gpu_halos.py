@@ -125,5 +125,38 @@ def test_read_radius_too_small_status():
     _run(data, H, cp, SO4[:1], [], flags=0, dmo=False)
 
 
+def test_reread_loop_finishes_every_halo_like_one_generous_read():
+    """run_chunks(reread=True): halos flagged status 1 are re-read with the returned radii
+    (chunk_tasks.py:188-367) and end with the rows a generous read radius gives directly"""
+    from soap_b200 import chunk_tasks as ct
+    from soap_b200.halo_tasks import DeviceChunk, process_halos
+
+    L = 20.0
+    cp = synth.coordinate_unit_params(L)
+    data, H = synth.dummy_chunk(77, 12, boxsize=L, n_background=20000, npart_choices=(100, 1000))
+    cfg = cmp.device_config(cp, so=SO4[:2], flags=8, dmo=False)
+    passes = []
+
+    def compute(cd, hc):
+        passes.append(len(hc["index"]))
+        return process_halos(DeviceChunk(cd, L), cfg, hc).table
+
+    big = dict(H)
+    big["read_radius"] = np.full(len(H["index"]), 8.0)
+    ref, iref = ct.run_chunks(data, big, L, 2, compute)
+    passes.clear()
+    small = dict(H)
+    small["read_radius"] = np.maximum(H["search_radius"], 0.3)
+    got, igot = ct.run_chunks(data, small, L, 2, compute, reread=True)
+    assert np.array_equal(iref.cpu().numpy(), igot.cpu().numpy())
+    ref, got = ref.cpu().numpy(), got.cpu().numpy()
+    assert (ref[:, 0] == 0).all() and (got[:, 0] == 0).all()
+    assert len(passes) > 2 and passes[-1] < passes[0]  # later passes only repeat the unfinished halos
+    # same property columns; the InputHalos columns (rungs walked, accepted radius, pairs) depend on
+    # where the ladder was clamped by read_radius, in the reference too (halo_tasks.py:166-181)
+    cols = list(range(6, ref.shape[1]))
+    np.testing.assert_allclose(got[:, cols], ref[:, cols], rtol=1e-12, atol=1e-12)
+
+
 def cmp_flags(kin=False, tens=False, hmr=False):
     return (1 if kin else 0) | (4 if tens else 0) | (8 if hmr else 0)
