@@ -16,10 +16,10 @@ pytestmark = pytest.mark.gpu
 SO4 = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
 
 
-def _process(data, halos, cp, L, no_tiers=False, fine_ppc=0):
+def _process(data, halos, cp, L, no_tiers=False, fine_ppc=0, cfg=None):
     from soap_b200.halo_tasks import DeviceChunk, process_halos
 
-    cfg = cmp.device_config(cp, so=SO4, flags=8, dmo=True)
+    cfg = cfg or cmp.device_config(cp, so=SO4, flags=8, dmo=True)
     if no_tiers:
         os.environ["SOAP_B200_NO_TIERS"] = "1"
     try:
@@ -58,6 +58,30 @@ def test_tiers_and_general_path_agree():
     b, sb, pb = _process(data, halos, cp, L, no_tiers=True)
     assert np.array_equal(sa, sb) and pa == pb
     _assert_same(a, b, INT_KEYS)
+
+
+def test_tiers_and_general_path_agree_hydro_kappa_iterative():
+    """the same cross-check for a config-3-like hydro chunk with every property group on:
+    kinematics, kappa_corot / stellar rotation (inside the warp tiers vs k_kappa), tensors,
+    half-mass radii, and the iterative tensors of the post-pass"""
+    L = 40.0
+    cp = synth.coordinate_unit_params(L)
+    data, halos = synth.nfw_chunk(600000, 1500, L, seed=33, device="cuda", max_np=50000,
+                                  type_fractions={0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001})
+    aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 100.0) for incl in (0, 1)]
+    cfg = cmp.device_config(cp, so=SO4[:2], apertures=aps, flags=1 | 2 | 4 | 8 | 16, dmo=False)
+    a, sa, pa = _process(data, halos, cp, L, cfg=cfg)
+    b, sb, pb = _process(data, halos, cp, L, no_tiers=True, cfg=cfg)
+    assert np.array_equal(sa, sb) and pa == pb and (sa == 0).sum() > 1000
+    for k in a:
+        x, y = a[k], b[k]
+        if k.split("/")[-1] in INT_KEYS:
+            assert np.array_equal(x, y), k
+            continue
+        # second moments about a mean cancel: compare on the scale of the column
+        sc = np.maximum(np.abs(y), 1e-6 * np.nanmax(np.abs(y)) + 1e-300)
+        bad = np.abs(x - y) > 1e-7 * sc
+        assert not bad.any(), (k, np.argwhere(bad)[:5], x[bad][:5], y[bad][:5])
 
 
 def test_config2_full_size_invariants():
