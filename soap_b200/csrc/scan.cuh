@@ -24,8 +24,11 @@ __device__ __forceinline__ int gtid() {
 }
 // CTA-wide alignment barrier of the lock-step tiers (named barrier 1): keeps the
 // warps of a CTA in the same code region so that they share instruction fetches.
-__device__ __forceinline__ void align_bar() {
-    asm volatile("barrier.sync 1, %0;" ::"r"(blockDim.x) : "memory");
+#ifndef SOAP_ALIGN_LEVEL
+#define SOAP_ALIGN_LEVEL 2
+#endif
+__device__ __forceinline__ void align_bar(int level = 1) {
+    if (level <= SOAP_ALIGN_LEVEL) asm volatile("barrier.sync 1, %0;" ::"r"(blockDim.x) : "memory");
 }
 
 // -------------------------------------------------------------- scan pass
@@ -594,7 +597,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         }
         gsync<NT>();
 
-        if (ALIGN) align_bar();
+        if (ALIGN) align_bar(2);
         // ------------- rank 0: the SO solves, one lane per SO variation (they are independent;
         // the sequential commit logic below consumes them in halo_prop_list order)
         if (crank == 0 && gt < n_so) {
@@ -810,7 +813,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         const bool so_committed = n_so > 0 && S.commit_hi_ > S.commit_lo_ && S.commit_lo_ < c_ap_lo && S.commit_hi_ > c_so_lo;
         const bool ap_committed = n_ap > 0 && S.commit_hi_ > c_ap_lo && S.commit_hi_ > S.commit_lo_;
         const bool need_c = S.fail_ < 2 && (so_committed || (ap_committed && want_hmr));
-        if (ALIGN) align_bar();
+        if (ALIGN) align_bar(2);
         // (uniform over the cluster: everyone leaves or everyone stays)
         if (!need_c) { csync(); return; }
 

@@ -354,15 +354,20 @@ template <int NCH, int V, int CAP>
 struct __align__(16) WarpSlot {
     Rec rec[CAP];
     uint32_t pid[CAP];
-    ScanShared<NCH, 32> S;
+    // the scan scratch (phase 3) and the moment staging tile (phase 4) are never live together
+    union {
+        ScanShared<NCH, 32> S;
+        struct {
+            double stage[32 * BankAcc<V>::VP];
+            int skey[32];
+        };
+    };
     Cuts cuts;
     DimRanges rg[3];
     uint32_t row_s0[32], row_off[33];
     unsigned long long minr;
     int32_t minfof;
     unsigned int n_stage;
-    int skey[32];
-    double stage[32 * BankAcc<V>::VP];
     // followed by bank_stride doubles of banks
 };
 
@@ -627,13 +632,14 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_small_warps(ChunkView v, HaloA
                                                                           &W.minfof, 1u);
             __syncwarp();
         } else {
-            align_bar();
-            align_bar();
+            align_bar(2);
+            align_bar(2);
         }
         align_bar();
         // ============ phase 4: moments of the committed properties + result row
         if (state == WS_TRY) {
             const int c_lo = W.S.commit_lo_, c_hi = W.S.commit_hi_, fail = W.S.fail_;
+            __syncwarp();  // W.S is dead from here: its storage becomes the staging tile
             if (c_hi > c_lo && fail < 2) {
                 const ScanRes* sr = ha.sres + h;
                 const bool sub_c = cfg.do_sub && c_lo == 0;
