@@ -45,6 +45,23 @@ def test_layout_is_pure_host_logic():
     assert ncol == sum(w for _, w in cols.values())
     # halo_tasks.py:306-317: the lowest threshold sets the target density
     assert cfg.target_density() == 200.0 * 0.3
+    # property_flags bit 4: the iterative tensor pair next to the non-iterative one, per block
+    # (BoundSubhalo, 2 SO, 2 apertures) and per projection axis
+    cfg_it = HaloPropConfig(boxsize=10.0, G=1.0, critical_density=1.0, mean_density=0.3,
+                            so=[("crit", 200.0), ("mean", 200.0)],
+                            apertures=[(0.05, 0.03, 0), (0.05, 0.03, 1)], projected=[(0.03, 0.03)],
+                            property_flags=1 | 4 | 8 | 16)
+    cfg_no = HaloPropConfig(boxsize=10.0, G=1.0, critical_density=1.0, mean_density=0.3,
+                            so=[("crit", 200.0), ("mean", 200.0)],
+                            apertures=[(0.05, 0.03, 0), (0.05, 0.03, 1)], projected=[(0.03, 0.03)],
+                            property_flags=1 | 4 | 8)
+    n_it, c_it = result_layout(cfg_it.to_c())
+    n_no, c_no = result_layout(cfg_no.to_c())
+    assert n_it - n_no == 5 * 12 + 3 * 6
+    assert c_it["BoundSubhalo/TotalInertiaTensorReduced"][1] == 6
+    assert c_it["Aperture/0/StellarInertiaTensor"][1] == 6
+    assert c_it["ProjectedAperture/0/projy/ProjectedTotalInertiaTensor"][1] == 3
+    assert "SO/0/TotalInertiaTensor" not in c_no
 
 
 def test_no_product_import_of_oracle():
