@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(TB) k_cell_keys(const double* __restrict__ pos
     int cy = cell_coord(pos[3 * i + 1], g.pmin[1], g.cs[1], g.res);
     int cz = cell_coord(pos[3 * i + 2], g.pmin[2], g.cs[2], g.res);
     key[i] = (uint32_t)cx + (uint32_t)g.res * ((uint32_t)cy + (uint32_t)g.res * (uint32_t)cz);
-    if (val) val[i] = base + (uint32_t)i;  // bits > 0: the first radix pass makes the indices up
+    val[i] = base + (uint32_t)i;
 }
 
 // cell_off[c] = first sorted position whose key is >= c (cell_off[ncell] = n)
@@ -181,8 +181,6 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     g.res = res;
 #define CK(stmt) do { if ((stmt) != 0) { soap_chunk_destroy(c); return -1; } } while (0)
 #define CKL(...) do { auto _f = [&]() -> int { __VA_ARGS__; return 0; }; if (_f() != 0) { soap_chunk_destroy(c); return -1; } } while (0)
-    int sort_bits = 0;
-    while ((1ll << sort_bits) < ncell) sort_bits++;
     c->create_log.begin("mesh_keys", stream);
     TypesIn tin;
     tin.n = 0;
@@ -190,7 +188,7 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     for (int t = 0; t < n_types; t++) {
         if (types[t].n == 0) continue;
         CKL(LAUNCH(h, k_cell_keys, grid_for(types[t].n, TB), TB, 0, stream, types[t].pos, types[t].n, g, key + base,
-                   sort_bits > 0 ? (uint32_t*)nullptr : val + base, (uint32_t)base));
+                   val + base, (uint32_t)base));
         uint8_t tc = (uint8_t)ptype_code(types[t].ptype);
         c->type_present[tc] = 1;
         TypeIn& T = tin.t[tin.n++];
@@ -202,7 +200,9 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     c->create_log.end(stream);
     c->create_log.begin("mesh_sort", stream);
     {
-        CK(radix_sort_pairs(h, key, val, key2, val2, ghist, (uint32_t)n, sort_bits, &key, &val, stream, 1));
+        int bits = 0;
+        while ((1ll << bits) < ncell) bits++;
+        CK(radix_sort_pairs(h, key, val, key2, val2, ghist, (uint32_t)n, bits, &key, &val, stream));
     }
     CKL(LAUNCH(h, k_cell_offsets, grid_for(n + 1, TB), TB, 0, stream, key, (uint32_t)n, (uint32_t)ncell, cell_off));
     c->create_log.end(stream);

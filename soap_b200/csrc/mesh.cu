@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TB) k_cell_key(const double* __restrict__ pos,
     const int32_t c = cx + g.res * cy + g.res * g.res * cz;  // shared_mesh.py:73-77
     if (cell_idx) cell_idx[i] = c;
     key[i] = (uint32_t)c;
-    if (val) val[i] = (uint32_t)i;  // bits > 0: the first radix pass makes the indices up
+    val[i] = (uint32_t)i;
 }
 
 // cell_offset[c] = first sorted position with key >= c; cell_count from consecutive offsets
@@ -311,12 +311,11 @@ int soap_mesh_build(soap_handle* h, const double* pos_dev, int64_t n, int resolu
     WS_GET(val2, uint32_t, h, "mesh_val2", n);
     WS_GET(ghist, uint32_t, h, "mesh_ghist", (size_t)RS_NB * nblk);
     WS_GET(offset_ext, int64_t, h, "mesh_offset_ext", ncell + 1);
+    LAUNCH(h, k_cell_key, grid_for(n, TB), TB, 0, stream, pos_dev, n, g, cell_idx_dev, key, val);
     int bits = 0;
     while ((1ll << bits) < ncell) bits++;
-    LAUNCH(h, k_cell_key, grid_for(n, TB), TB, 0, stream, pos_dev, n, g, cell_idx_dev, key,
-           bits > 0 ? (uint32_t*)nullptr : val);
     uint32_t *ks = nullptr, *vs = nullptr;
-    if (radix_sort_pairs(h, key, val, key2, val2, ghist, (uint32_t)n, bits, &ks, &vs, stream, 1)) return -1;
+    if (radix_sort_pairs(h, key, val, key2, val2, ghist, (uint32_t)n, bits, &ks, &vs, stream)) return -1;
     LAUNCH(h, k_cell_bounds, grid_for(n + 1, TB), TB, 0, stream, ks, (uint32_t)n, (uint32_t)ncell, offset_ext);
     LAUNCH(h, k_cell_counts, grid_for(ncell, TB), TB, 0, stream, offset_ext, ncell, cell_count_dev, cell_offset_dev);
     LAUNCH(h, k_widen_idx, grid_for(n, TB), TB, 0, stream, vs, n, sort_idx_dev);

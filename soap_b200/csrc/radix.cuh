@@ -46,7 +46,7 @@ static __global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __r
         const uint32_t i = wbeg + r * 32 + lane;
         const bool ok = i < n;
         k_[r] = ok ? key_in[i] : 0xffffffffu;
-        v_[r] = ok ? (val_in ? val_in[i] : i) : 0u;  // first pass: the values are the element indices
+        v_[r] = ok ? val_in[i] : 0u;
         const uint32_t d = ok ? ((k_[r] >> shift) & (RS_NB - 1)) : RS_NB;  // invalid lanes match each other only
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
@@ -85,19 +85,16 @@ static __global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __r
 
 // Sort n pairs by the low `bits` bits of the key (stable).  key/val and key2/val2 are ping-pong
 // buffers of n elements, ghist holds RS_NB * ceil(n / RS_TILE) counters.  Returns (through
-// key_out/val_out) the buffers that hold the sorted result.  iota != 0: the values are the element
-// indices 0..n-1 and `val` has not been written by the caller (the first pass makes them up;
-// bits must be > 0).
+// key_out/val_out) the buffers that hold the sorted result.
 static inline int radix_sort_pairs(soap_handle* h, uint32_t* key, uint32_t* val, uint32_t* key2, uint32_t* val2,
                                    uint32_t* ghist, uint32_t n, int bits, uint32_t** key_out, uint32_t** val_out,
-                                   cudaStream_t stream, int iota = 0) {
+                                   cudaStream_t stream) {
     const uint32_t nblk = (n + RS_TILE - 1) / RS_TILE;
     uint32_t *ki = key, *vi = val, *ko = key2, *vo = val2;
     for (int shift = 0; shift < bits; shift += 8) {
         LAUNCH(h, k_rs_hist, nblk, RS_TB, 0, stream, ki, n, shift, nblk, ghist);
         if (soap_exclusive_scan_u32(h, ghist, ghist, nullptr, (int64_t)RS_NB * nblk, nullptr, stream)) return -1;
-        LAUNCH(h, k_rs_scatter, nblk, RS_TB, 0, stream, ki, (iota && shift == 0) ? (const uint32_t*)nullptr : vi, n, shift,
-               nblk, ghist, ko, vo);
+        LAUNCH(h, k_rs_scatter, nblk, RS_TB, 0, stream, ki, vi, n, shift, nblk, ghist, ko, vo);
         uint32_t* t1 = ki; ki = ko; ko = t1;
         uint32_t* t2 = vi; vi = vo; vo = t2;
     }
