@@ -51,7 +51,7 @@ constexpr int FINE_TARGET = 12;  // expected records per fine radial bin (sorted
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
 // halos with up to this many bound particles start in fused tier 0 / 1 / 2; larger ones take the general path
-constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 300, SMALL_NEXP_2 = 800;
+constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 400, SMALL_NEXP_2 = 800;
 
 struct Bucket {
     unsigned long long start;
