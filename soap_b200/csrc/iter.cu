@@ -32,6 +32,7 @@ constexpr int IT_NV = 9;  // sum w, 6 weighted second moments, particles inside,
 struct __align__(8) ItState {
     double vec[9];   // eigenvectors: column j belongs to axis j
     double axis[3];  // ellipsoid semi-axes (coordinate units)
+    double iax[3];   // their reciprocals (the sweep multiplies; a division per lane and axis is the hot spot)
     double q;        // sqrt(eig_val[1] / eig_val[2]) of this pass
     double R;        // sphere radius (coordinate units)
     double Rs2;      // squared radius of the sphere the selection was committed with
@@ -105,6 +106,7 @@ __global__ void k_it_init(HaloArrays ha, DevCfg cfg, int64_t nh, int nsel, ItSta
         for (int k = 0; k < 9; k++) st.vec[k] = (k % 4 == 0) ? 1.0 : 0.0;
         if (sel.proj >= 0) { st.vec[3] = 1.0; st.vec[4] = 0.0; }  // 2x2 identity, row-major
         st.axis[0] = st.axis[1] = st.axis[2] = R;
+        st.iax[0] = st.iax[1] = st.iax[2] = 1.0 / R;
         st.q = 1.0;
         st.R = R;
         st.Rs2 = __dmul_rn(rs, rs);
@@ -178,13 +180,13 @@ __global__ void __launch_bounds__(TB) k_it_accum(ChunkView v, HaloArrays ha, Dev
                     const bool mem2 = member && !(red && nrm_s <= 1e-8);
                     bool inside;
                     if (proj < 0) {
-                        const double px = ((x * st.vec[0] + y * st.vec[3]) + z * st.vec[6]) / st.axis[0];
-                        const double py = ((x * st.vec[1] + y * st.vec[4]) + z * st.vec[7]) / st.axis[1];
-                        const double pz = ((x * st.vec[2] + y * st.vec[5]) + z * st.vec[8]) / st.axis[2];
+                        const double px = ((x * st.vec[0] + y * st.vec[3]) + z * st.vec[6]) * st.iax[0];
+                        const double py = ((x * st.vec[1] + y * st.vec[4]) + z * st.vec[7]) * st.iax[1];
+                        const double pz = ((x * st.vec[2] + y * st.vec[5]) + z * st.vec[8]) * st.iax[2];
                         inside = mem2 && sqrt((px * px + py * py) + pz * pz) <= 1.0;
                     } else {
-                        const double p0 = (pa * st.vec[0] + pb * st.vec[2]) / st.axis[0];
-                        const double p1 = (pa * st.vec[1] + pb * st.vec[3]) / st.axis[1];
+                        const double p0 = (pa * st.vec[0] + pb * st.vec[2]) * st.iax[0];
+                        const double p1 = (pa * st.vec[1] + pb * st.vec[3]) * st.iax[1];
                         inside = mem2 && sqrt(p0 * p0 + p1 * p1) <= 1.0;
                     }
                     const double w = inside ? m : 0.0;
@@ -310,6 +312,7 @@ __global__ void k_it_update(HaloArrays ha, DevCfg cfg, const uint32_t* __restric
             st.axis[0] = st.R * cbrt(sa * p);
             st.axis[1] = st.R * cbrt(q / p);
             st.axis[2] = st.R * (1.0 / cbrt(q * sa));
+            for (int k = 0; k < 3; k++) st.iax[k] = 1.0 / st.axis[k];
             for (int k = 0; k < 9; k++) st.vec[k] = vec[k];
         } else {
             // 2x2 symmetric [[aa, ab], [ab, bb]]: one Jacobi rotation, eigenvalues ascending (:300-341)
@@ -335,6 +338,7 @@ __global__ void k_it_update(HaloArrays ha, DevCfg cfg, const uint32_t* __restric
             st.q = q;
             st.axis[0] = st.R * sqrt(q);
             st.axis[1] = st.R * (1.0 / sqrt(q));
+            st.iax[0] = 1.0 / st.axis[0]; st.iax[1] = 1.0 / st.axis[1];
             st.vec[0] = v00; st.vec[1] = v01; st.vec[2] = v10; st.vec[3] = v11;
         }
         any = 1;
