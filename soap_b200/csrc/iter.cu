@@ -116,7 +116,7 @@ __global__ void k_it_init(HaloArrays ha, DevCfg cfg, int64_t nh, int nsel, ItSta
     if (gate) alive[h] = 1;
 }
 
-__global__ void __launch_bounds__(TB) k_it_accum(ChunkView v, HaloArrays ha, DevCfg cfg,
+__global__ void __launch_bounds__(TB, 3) k_it_accum(ChunkView v, HaloArrays ha, DevCfg cfg,
                                                  const Item* __restrict__ items,
                                                  const unsigned int* __restrict__ n_items_dev, int nsel,
                                                  const ItState* __restrict__ state, double* __restrict__ sums,
