@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
     }
 }
 
-__global__ void __launch_bounds__(TB) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
+__global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
                                               const unsigned int* __restrict__ n_items_dev) {
     __shared__ SweepShared SW;
     __shared__ KapSel sel[1 + SOAP_MAX_APERTURES];
