@@ -61,7 +61,7 @@ ALG_BYTES = {
     "scan_solve": 16,  # per record (one read of the sorted profile)
     "moments": 48,   # per pair: position 24, mass 4, velocity 12, grnr 4, fof 4
     # fused tiers (small.cu), per pair: the whole stage B+C figure of SURVEY.md 8(d)
-    "small_0": 48, "small_1": 48, "small_2": 48,
+    "tier_0": 48, "tier_1": 48,
 }
 
 
@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--fine-ppc", type=int, default=0)
+    ap.add_argument("--debug-flags", type=int, default=0, help="soap_halo_config.debug_flags (cross-check switches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
@@ -393,6 +394,7 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     handle = _lib.default_handle(local_rank)
     cfg = build_config(cp, so_list, args.workload)
+    cfg.debug_flags = args.debug_flags
     ncol, cols = result_layout(cfg.to_c())
     H = int(halos["cofp"].shape[0])
     table = torch.empty((H, ncol), dtype=torch.float64, device=dev)
@@ -510,9 +512,8 @@ def main():
         "sort": (stats.get("try_pairs", 0.0), ph.get("halos/sort", 0.0)),
         "scan_solve": (stats.get("try_pairs", 0.0), ph.get("halos/scan_solve", 0.0)),
         "moments": (stats.get("moment_pairs", 0.0), ph.get("halos/moments", 0.0)),
-        "small_0": (stats.get("small_pairs_0", 0.0), ph.get("halos/small_0", 0.0)),
-        "small_1": (stats.get("small_pairs_1", 0.0), ph.get("halos/small_1", 0.0)),
-        "small_2": (stats.get("small_pairs_2", 0.0), ph.get("halos/small_2", 0.0)),
+        "tier_0": (stats.get("small_pairs_0", 0.0), ph.get("halos/tier_0", 0.0)),
+        "tier_1": (stats.get("small_pairs_1", 0.0), ph.get("halos/tier_1", 0.0)),
     }
     kernels = {}
     for k, (n_units, t_ms) in units.items():
@@ -528,7 +529,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic,
-                "launches_per_step": 1 if dom.startswith("small") or dom == "mesh" else int(stats.get("rounds", 1))}
+                "launches_per_step": 1 if dom.startswith("tier") or dom == "mesh" else int(stats.get("rounds", 1))}
     total_alg = 32.0 * n_part + 48.0 * pairs + 8.0 * H * ncol
     kern_ms = sum(v["ms"] for v in kernels.values())
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SOAP_B200_ABI_VERSION 1
+#define SOAP_B200_ABI_VERSION 2
 
 /* per-halo status codes written by soap_process_halos */
 #define SOAP_HALO_OK 0
@@ -41,6 +41,7 @@ extern "C" {
 #define SOAP_MAX_SO 8
 #define SOAP_MAX_APERTURES 16
 #define SOAP_MAX_PTYPES 8
+#define SOAP_MAX_FILTERS 8
 
 typedef struct soap_handle soap_handle;
 typedef struct soap_mesh soap_mesh;
@@ -140,6 +141,28 @@ typedef struct {
      * 3-D inertia tensors (inertia_tensors.py:19-132, max_iterations = 20; needs bit 2) */
     uint32_t property_flags;
     int dmo;                  /* only dark matter present / requested */
+    /* CategoryFilter (SOAP/core/category_filter.py:69-110): filter f is satisfied when the sum of the
+     * BoundSubhalo particle counts of the types in filter_types[f] (bit 0 gas, 1 dm, 2 star, 3 bh) is
+     * >= filter_limit[f].  Index 0 is "basic" (always satisfied; its entries are ignored).  A variation
+     * whose halo_filter is not satisfied is left at exact zeros and never asks for a larger radius
+     * (SO_properties.py:3627, aperture_properties.py:4127, projected_aperture_properties.py:1888).
+     * Filters other than 0 need do_subhalo. */
+    int n_filters;                            /* including index 0; 0 or 1 = no filtering */
+    int64_t filter_limit[SOAP_MAX_FILTERS];
+    uint32_t filter_types[SOAP_MAX_FILTERS];
+    int so_filter[SOAP_MAX_SO];
+    int ap_filter[SOAP_MAX_APERTURES];
+    int proj_filter[SOAP_MAX_APERTURES];
+    /* skip_gt_enclose_radius (aperture_properties.py:4082-4123, projected_aperture_properties.py:1827-1888):
+     * radius of the previous aperture of the list in coordinate units, or < 0 when the shortcut is off /
+     * this is the first radius.  If it exceeds BoundSubhalo/EncloseRadius an inclusive or projected
+     * aperture is skipped (zeros) and an exclusive one equals the previous exclusive aperture, so it is
+     * computed from the particles already loaded without asking for a larger radius. */
+    double ap_prev_radius[SOAP_MAX_APERTURES];
+    double proj_prev_radius[SOAP_MAX_APERTURES];
+    /* cross-check switches, 0 in production: bit 0 = route every halo through the general
+     * (kernel-sequence) path instead of the small-halo tiers */
+    uint32_t debug_flags;
 } soap_halo_config;
 
 /* Column layout of the result table for a config: writes a '\n'-separated list

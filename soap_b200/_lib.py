@@ -17,6 +17,8 @@ CSRC = os.path.join(_HERE, "csrc")
 SOAP_MAX_SO = 8
 SOAP_MAX_APERTURES = 16
 SOAP_MAX_PTYPES = 8
+SOAP_MAX_FILTERS = 8
+ABI_VERSION = 2
 
 # per-halo status codes (include/soap_b200.h)
 HALO_OK, HALO_RADIUS_TOO_SMALL, HALO_COUNT_MISMATCH, HALO_SO_NOT_FOUND, HALO_ROOT_FAILED = range(5)
@@ -63,6 +65,15 @@ class HaloConfig(C.Structure):
         ("proj_physical_mpc", C.c_double * SOAP_MAX_APERTURES),
         ("property_flags", C.c_uint32),
         ("dmo", C.c_int),
+        ("n_filters", C.c_int),
+        ("filter_limit", C.c_int64 * SOAP_MAX_FILTERS),
+        ("filter_types", C.c_uint32 * SOAP_MAX_FILTERS),
+        ("so_filter", C.c_int * SOAP_MAX_SO),
+        ("ap_filter", C.c_int * SOAP_MAX_APERTURES),
+        ("proj_filter", C.c_int * SOAP_MAX_APERTURES),
+        ("ap_prev_radius", C.c_double * SOAP_MAX_APERTURES),
+        ("proj_prev_radius", C.c_double * SOAP_MAX_APERTURES),
+        ("debug_flags", C.c_uint32),
     ]
 
 
@@ -130,7 +141,7 @@ def lib():
         fn = getattr(L, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if L.soap_abi_version() != 1:
+    if L.soap_abi_version() != ABI_VERSION:
         raise SoapError("libsoap_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -16,13 +16,21 @@
 //                  (kinematic_properties.py:555-593), half-mass radii
 //                  (half_mass_radius.py:16-97); decides retry vs final
 //   k_moments      (moments.cu) masked moment sums + result row
+#include "moments.cuh"
 #include "scan.cuh"
 
 #include <stdlib.h>
 
 int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
-                        const unsigned int* n_items_dev, unsigned int n_items_host,
-                        unsigned int n_mslot, unsigned int grid, cudaStream_t stream);
+                        const unsigned int* n_items_dev, unsigned int n_items_host, unsigned int grid,
+                        cudaStream_t stream);
+int soap_bank_stride(const DevCfg& cfg);
+int soap_launch_rows(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
+                     const unsigned int* n_list_dev, unsigned int n_list_host, cudaStream_t stream);
+int soap_launch_solve_seq(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
+                          const unsigned int* n_list_dev, unsigned int n_list_host, const Rec* recs, uint32_t* next,
+                          unsigned int* n_next, Counters* ctr, const unsigned long long* item_minr, const int32_t* item_minfof,
+                          cudaStream_t stream);
 int soap_write_input_cols(soap_handle* h, const HaloArrays& ha, int64_t nh, cudaStream_t stream);
 int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
                       const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* acc_list,
@@ -37,10 +45,10 @@ int soap_launch_iter_tensors(soap_chunk* c, const DevCfg& cfg, const HaloArrays&
                              const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* list,
                              const unsigned int* n_list_dev, unsigned int n_list_host, unsigned int grid,
                              cudaStream_t stream);
-int soap_small_tier_fits(const DevCfg& cfg, int tier);
-int soap_launch_small(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, int tier, const uint32_t* list,
-                      const unsigned int* n_list, unsigned int n_list_upper, uint32_t* overflow,
-                      unsigned int* n_overflow, unsigned int* queue_cursor, Counters* ctr, cudaStream_t stream);
+int soap_tier_round(soap_chunk* c, const DevCfg& cfg, HaloArrays& ha, int tier, const uint32_t* list,
+                    const unsigned int* n_list, unsigned int n_upper, uint32_t* overflow, unsigned int* n_overflow,
+                    unsigned int* queue_cursor, uint32_t* try_list, uint32_t* next, unsigned int* n_next, Counters* ctr,
+                    unsigned long long* item_minr, int32_t* item_minfof, cudaStream_t stream);
 
 namespace {
 
@@ -49,9 +57,12 @@ constexpr int SB_CAP = 4096;     // records of one bucket sorted in shared memor
 constexpr int SMALL_CAP = 512;   // small-bucket class (8 KB)
 constexpr int FINE_TARGET = 12;  // expected records per fine radial bin (sorted by one warp in registers)
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
+constexpr uint32_t SEQ_MAX = 512;     // halos with up to this many records are scanned by one thread each (seq.cuh)
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
-// halos with up to this many bound particles start in fused tier 0 / 1 / 2; larger ones take the general path
-constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 400, SMALL_NEXP_2 = 800;
+// halos with up to this many bound particles start in tier 0 / 1 of the staged small-halo path (tier.cu:
+// spheres of up to 256 / 1024 particles); larger ones take the general path
+constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 500;
+constexpr int TIER_ROUNDS = 3;
 
 struct Bucket {
     unsigned long long start;
@@ -133,7 +144,7 @@ __global__ void k_tier_place(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_
 __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
                                                     const unsigned int* __restrict__ n_pend,
                                                     Item* __restrict__ items, unsigned int items_cap,
-                                                    Counters* ctr, int look, int replan) {
+                                                    Counters* ctr, int look, int replan, int bank_stride) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_pend) return;
     const uint32_t h = pend[it];
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, 
         ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
     }
     ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
+    if (replan) ha.bank_off[h] = (unsigned long long)atomicAdd(&ctr->n_bslot, 1u) * (unsigned long long)bank_stride;
     if (ni == 1) {
         Item im;
         im.halo = h; im.first = 0; im.count = (uint32_t)cand; im.row0 = 0;
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
                                               uint32_t* __restrict__ big_list,
                                               uint32_t* __restrict__ acc_list,
                                               uint32_t* __restrict__ multi_list,
+                                              uint32_t* __restrict__ seq_list,
                                               uint32_t* __restrict__ next, Counters* ctr) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_pend) return;
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
         ha.rung_r[h] = ha.cur_r[h];
         const uint32_t cnt = ha.cnt[h];
         if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // scanned by a CTA cluster
+        else if (cnt <= SEQ_MAX) seq_list[atomicAdd(&ctr->n_seq, 1u)] = h;  // by one thread
         else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
         acc_list[atomicAdd(&ctr->n_acc, 1u)] = h;  // every accepted halo: its sweep is planned again
         ha.state[h] = ST_TRY;
@@ -432,7 +446,7 @@ __global__ void k_multi_offsets(HaloArrays ha, const uint32_t* __restrict__ mult
     ha.rec_off[h] = ctr->rec_single + (unsigned long long)fine_excl[ha.fine_off[h]];
 }
 
-// single-bucket halos -> bucket lists (thread per try halo)
+// single-bucket halos -> bucket lists (thread per accepted halo)
 __global__ void k_single_buckets(HaloArrays ha, const uint32_t* __restrict__ try_list,
                                  const unsigned int* __restrict__ n_try, Counters* ctr,
                                  Bucket* __restrict__ bkt_small, Bucket* __restrict__ bkt_big) {
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevC
         const double R = ha.cur_r[h];
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
         const uint32_t nf = ha.nfine[h];
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         Rec* out = recs + (nf ? ctr->rec_single : ha.rec_off[h]);
         const int64_t* fex = fine_excl + (nf ? ha.fine_off[h] : 0);
         uint32_t* fcur = fine_cursor + (nf ? ha.fine_off[h] : 0);
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(TB) k_pj_bins(ChunkView v, HaloArrays ha, DevC
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.rung_r[h];
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         uint32_t* fc = fine_cnt + pl.fine_off[h];
         const int64_t* fex = FILL ? fine_excl + pl.fine_off[h] : nullptr;
         const bool dmo = cfg.dmo != 0;
@@ -753,7 +767,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ?
     for (unsigned int it = cid; it < *n_try; it += ncl) {
         const uint32_t h = try_list[it];
         const uint32_t ib = ha.item_base[h];
-        scan_solve_halo<NCH, CS, SCAN_NT, SCAN_K>(S, ha, cfg, h, ha.cnt[h], recs + ha.rec_off[h], next, ctr,
+        scan_solve_halo<NCH, CS, SCAN_NT, (CS > 1 ? 2 * SCAN_K : SCAN_K)>(S, ha, cfg, h, ha.cnt[h], recs + ha.rec_off[h], next, ctr,
                                                   item_minr + ib, item_minfof + ib, ha.n_items[h]);
     }
 }
@@ -924,6 +938,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(rung_cnt, uint32_t, h, "h_rung_cnt", (size_t)H * LOOK_MAX); ha.rung_cnt = rung_cnt;
     WS_GET(rung_msum, double, h, "h_rung_msum", (size_t)H * LOOK_MAX); ha.rung_msum = rung_msum;
     WS_GET(multi_list, uint32_t, h, "h_multi", H);
+    WS_GET(seq_list, uint32_t, h, "h_seq", H);
+    WS_GET(bank_off, unsigned long long, h, "h_bank_off", H); ha.bank_off = bank_off;
+    WS_GET(cuts_arr, Cuts, h, "h_cuts", H); ha.cuts = cuts_arr;
+    ha.gbank = nullptr;
+    const int bank_stride = soap_bank_stride(dc);
     WS_GET(ctr, Counters, h, "h_ctr", 8);  // [0] current round, [2..4] the fused tiers
     WS_GET(n_pend_dev, unsigned int, h, "h_npend", 4);
     // work items: every halo has at least one; large spheres are cut every ITEM_CAND candidates
@@ -939,87 +958,86 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     c->last_rounds = 0;
     uint32_t* pend = listA;
     uint32_t* next = listB;
-    // tiers: fused small-halo kernels first (small.cu), the rest and their overflow below
-    constexpr int NTIER = 3;
-    long long tier_nexp[NTIER] = {SMALL_NEXP_0, SMALL_NEXP_1, SMALL_NEXP_2};
-    if (const char* e = getenv("SOAP_B200_TIER_NEXP")) {  // tuning switch: "a,b,c"
-        long long a = 0, b = 0, cc = 0;
-        if (sscanf(e, "%lld,%lld,%lld", &a, &b, &cc) == 3 && a <= b && b <= cc && cc < TIER_BUCKETS) {
-            tier_nexp[0] = a; tier_nexp[1] = b; tier_nexp[2] = cc;
-        }
-    }
-    uint32_t* tier_list[NTIER + 1];
+    // tiers: the staged small-halo path first (tier.cu), the rest and its overflow below
+    constexpr int NTIER = 2;
+    const long long tier_nexp[NTIER] = {SMALL_NEXP_0, SMALL_NEXP_1};
+    uint32_t* tier_list[3 + 1];
     WS_GET(list0, uint32_t, h, "h_list0", H); tier_list[0] = list0;
     WS_GET(list1, uint32_t, h, "h_list1", H); tier_list[1] = list1;
-    WS_GET(list2, uint32_t, h, "h_list2", H); tier_list[2] = list2;
-    tier_list[NTIER] = pend;
-    WS_GET(tier_n, unsigned int, h, "h_tier_n", 16);  // [0..3] list sizes, [8..10] queue cursors
+    WS_GET(list2, uint32_t, h, "h_list2", H); tier_list[2] = list2;  // unused third size class of k_tier_place
+    WS_GET(tier_n, unsigned int, h, "h_tier_n", 16);  // [0..3] list sizes, [8..] queue cursor, [12] round list size
     CUDA_TRY(cudaMemsetAsync(tier_n, 0, 16 * sizeof(unsigned int), stream));
-    CUDA_TRY(cudaMemsetAsync(ctr + 2, 0, NTIER * sizeof(Counters), stream));
+    CUDA_TRY(cudaMemsetAsync(ctr + 2, 0, sizeof(Counters), stream));
     TierLims tl;
-    bool tier_on[NTIER];
-    {
-        long long prev = -1;
-        for (int t = 0; t < NTIER; t++) {
-            tier_on[t] = soap_small_tier_fits(dc, t) != 0 && !((dc.flags & PF_KAPPA) && !dc.dmo && t == 2) && dc.n_pj == 0 &&
-                         getenv("SOAP_B200_NO_TIERS") == nullptr;  // debugging / cross-check switch
-            tl.lim[t] = tier_on[t] ? tier_nexp[t] : prev;  // a disabled tier takes no halos
-            prev = tl.lim[t];
-        }
-    }
-    for (int t = 0; t < NTIER; t++)
+    // projected apertures and the general-path cross-check switch keep every halo out of the tiers
+    const bool tiers_on = dc.n_pj == 0 && !(cfg->debug_flags & 1u);
+    for (int t = 0; t < 3; t++) tl.lim[t] = tiers_on ? tier_nexp[t < NTIER ? t : NTIER - 1] : -1;
+    for (int t = 0; t < 3; t++)
         if (tl.lim[t] >= TIER_BUCKETS) SOAP_FAIL("soap_process_halos: tier limit above %d", TIER_BUCKETS - 1);
     WS_GET(size_hist, unsigned int, h, "h_size_hist", 2 * TIER_BUCKETS);
     CUDA_TRY(cudaMemsetAsync(size_hist, 0, 2 * TIER_BUCKETS * sizeof(unsigned int), stream));
     LAUNCH(h, k_init, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, pend, tier_n, size_hist, tl);
-    if (tl.lim[NTIER - 1] >= 0) {
+    unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
+    for (int t = 0; t < 3; t++) c->last_tier_pairs[t] = 0;
+    if (tiers_on) {
         LAUNCH(h, k_tier_scan, 1, TIER_BUCKETS, 0, stream, size_hist, tier_n, tl);
         LAUNCH(h, k_tier_place, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, list0, list1, list2,
                size_hist + TIER_BUCKETS, size_hist, tl);
-    }
-    for (int t = 0; t < NTIER; t++) {
-        if (!tier_on[t]) continue;
-        int to = t + 1;  // overflow goes to the next enabled tier, else to the general path
-        while (to < NTIER && !tier_on[to]) to++;
-        static const char* names[NTIER] = {"small_0", "small_1", "small_2"};
-        log.begin(names[t], stream);
-        if (soap_launch_small(c, dc, ha, t, tier_list[t], tier_n + t, H, tier_list[to], tier_n + to, tier_n + 8 + t,
-                              ctr + 2 + t, stream) < 0)
-            return -1;
-        log.end(stream);
+        Counters* tctr = ctr + 2;
+        uint32_t* round_next[2] = {listB, big_list};  // free until the general path starts
+        for (int t = 0; t < NTIER; t++) {
+            // overflow goes to the next tier, from the last one to the general path's pending list
+            uint32_t* ovf = t + 1 < NTIER ? tier_list[t + 1] : pend;
+            unsigned int* n_ovf = t + 1 < NTIER ? tier_n + t + 1 : tier_n + 3;
+            unsigned int n_host = 0;
+            CUDA_TRY(cudaMemcpyAsync(&n_host, tier_n + t, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            const uint32_t* list = tier_list[t];
+            const unsigned int* n_dev = tier_n + t;
+            for (int round = 0; n_host > 0; round++) {
+                if (round > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
+                CUDA_TRY(cudaMemsetAsync(tctr, 0, sizeof(Counters), stream));
+                CUDA_TRY(cudaMemsetAsync(tier_n + 8, 0, sizeof(unsigned int), stream));
+                log.begin(t == 0 ? "tier_0" : "tier_1", stream);
+                // stragglers that still ask for a larger radius after TIER_ROUNDS rounds move on like overflow:
+                // a handful of halos climbing the ladder one launch sequence per rung is what the general
+                // path's 12-rung look-ahead is for
+                const bool last = round + 1 >= TIER_ROUNDS;
+                if (soap_tier_round(c, dc, ha, t, list, n_dev, n_host, ovf, n_ovf, tier_n + 8, try_list,
+                                    last ? ovf : round_next[round & 1], last ? n_ovf : &tctr->n_next, tctr, item_minr,
+                                    item_minfof, stream) < 0)
+                    return -1;
+                log.end(stream);
+                Counters tc;
+                CUDA_TRY(cudaMemcpyAsync(tier_n + 12, &tctr->n_next, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
+                CUDA_TRY(cudaMemcpyAsync(&tc, tctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                total_pairs += tc.pairs;
+                total_cand += tc.candidates;
+                c->last_tier_pairs[t] += (int64_t)tc.pairs;
+                list = round_next[round & 1];
+                n_dev = tier_n + 12;
+                n_host = tc.n_next;
+            }
+        }
     }
     unsigned int n_pend = 0;
-    CUDA_TRY(cudaMemcpyAsync(n_pend_dev, tier_n + NTIER, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(&n_pend, tier_n + NTIER, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    Counters small_ctr[NTIER];
-    CUDA_TRY(cudaMemcpyAsync(small_ctr, ctr + 2, NTIER * sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(n_pend_dev, tier_n + 3, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(&n_pend, tier_n + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    const int sm = h->sm_count;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(k_sort_bucket<SB_CAP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(SB_CAP * sizeof(Rec))));
-        attr_done = true;
-    }
-    const unsigned int sweep_grid = (unsigned)(sm * 6);  // persistent CTAs striding over the item list
-    unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
-    for (int t = 0; t < NTIER; t++) {
-        total_pairs += small_ctr[t].pairs;
-        total_cand += small_ctr[t].candidates;
-    }
     c->last_small_pairs = (int64_t)total_pairs;
-    for (int t = 0; t < NTIER; t++) c->last_tier_pairs[t] = (int64_t)small_ctr[t].pairs;
-    const bool trace = getenv("SOAP_B200_TRACE") != nullptr;
-    if (trace)
-        fprintf(stderr, "[soap_b200] tiers: lists %u %u %u -> general %u | small pairs %llu %llu %llu\n", 0u, 0u, 0u, n_pend,
-                (unsigned long long)small_ctr[0].pairs, (unsigned long long)small_ctr[1].pairs, (unsigned long long)small_ctr[2].pairs);
+    const int sm = h->sm_count;
+    // per device, so set on every call (cheap)
+    CUDA_TRY(cudaFuncSetAttribute(k_sort_bucket<SB_CAP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SB_CAP * sizeof(Rec))));
+    const unsigned int sweep_grid = (unsigned)(sm * 6);  // persistent CTAs striding over the item list
     // plan a sweep per halo of `list`; coarse meshes / huge spheres can need more
     // work items than provisioned: grow the list and plan again
     auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int look, int replan) -> int {
         for (int attempt = 0; attempt < 2; attempt++) {
-            CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 3 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow
+            CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 4 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow, n_bslot
             LAUNCH(h, k_plan_items, grid_for(n_host, 128), 128, 0, stream, v, ha, list, n_dev, items,
-                   (unsigned int)items_cap, ctr, look, replan);
+                   (unsigned int)items_cap, ctr, look, replan, bank_stride);
             Counters pc;
             CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1049,7 +1067,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
-               acc_list, multi_list, next, ctr);
+               acc_list, multi_list, seq_list, next, ctr);
         log.end(stream);
         Counters hc;
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -1057,8 +1075,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
-        if (hc.n_try + hc.n_big > 0) {
-            const unsigned int n_try = hc.n_try + hc.n_big;
+        if (hc.n_try + hc.n_big + hc.n_seq > 0) {
+            const unsigned int n_try = hc.n_try + hc.n_big + hc.n_seq;
             // the accepted radius is generally smaller than the swept one: plan its sweep
             log.begin("plan", stream);
             if (plan(acc_list, &ctr->n_acc, n_try, look, 1)) return -1;
@@ -1068,6 +1086,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             // workspace for this round
             Rec* recs = (Rec*)h->get("h_recs", sizeof(Rec) * (size_t)(hc.rec_total + 1));
             if (!recs) return -1;
+            ha.gbank = (double*)h->get("h_gbank", sizeof(double) * (size_t)bank_stride * (hc.n_bslot + 1));
+            if (!ha.gbank) return -1;
+            CUDA_TRY(cudaMemsetAsync(ha.gbank, 0, sizeof(double) * (size_t)bank_stride * hc.n_bslot, stream));
             // single-bin halos give one bucket each; bins above BIN_SMEM records (k_sort_bins) one each
             const size_t max_bkt = (size_t)n_try + (size_t)(hc.rec_total / BIN_SMEM) + 16;
             Bucket* bkt_small = (Bucket*)h->get("h_bkt_small", sizeof(Bucket) * max_bkt);
@@ -1088,9 +1109,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                        fine_excl, ctr);
                 log.end(stream);
             }
-            if (hc.n_try > 0)
-                LAUNCH(h, k_single_buckets, grid_for(hc.n_try, 128), 128, 0, stream, ha, try_list, n_try_dev, ctr,
-                       bkt_small, bkt_big);
+            LAUNCH(h, k_single_buckets, grid_for(n_try, 128), 128, 0, stream, ha, acc_list, &ctr->n_acc, ctr, bkt_small,
+                   bkt_big);
             log.begin("collect", stream);
             LAUNCH(h, k_collect, sweep_grid, TB, 0, stream, v, ha, dc, items, fine_excl, fine_cur, ctr, recs,
                    item_minr, item_minfof);
@@ -1115,6 +1135,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             }
             log.end(stream);
             log.begin("scan_solve", stream);
+            if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr, item_minfof,
+                                      stream))
+                return -1;
             if (hc.n_try > 0) {
                 unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
                 if (cfg->dmo)
@@ -1136,7 +1159,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             }
             log.end(stream);
             log.begin("moments", stream);
-            if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
+            if (soap_launch_moments(c, dc, ha, items, &ctr->n_items, hc.n_items, sweep_grid, stream)) return -1;
+            if (soap_launch_rows(c, dc, ha, acc_list, &ctr->n_acc, n_try, stream)) return -1;
             if (soap_launch_projected(c, dc, ha, items, &ctr->n_items, hc.n_items, hc.n_mslot, sweep_grid, stream)) return -1;
             if (dc.n_pj > 0 && (dc.flags & PF_HMR)) {
                 // projected half-mass radii: per axis bin by projected radius, sort the bins, scan
@@ -1189,11 +1213,6 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         CUDA_TRY(cudaStreamSynchronize(stream));
         total_pairs += hc2.pairs;
         total_mom_pairs += hc2.mom_pairs;
-        if (trace)
-            fprintf(stderr, "[soap_b200] round %d: pend %u items %u cand %llu in-sphere %llu | try %u big %u multi %u recs %llu | final-pairs %llu next %u\n",
-                    c->last_rounds, n_pend, hc.n_items, (unsigned long long)hc.candidates,
-                    (unsigned long long)hc.count_pairs, hc.n_try, hc.n_big, hc.n_multi,
-                    (unsigned long long)hc.rec_total, (unsigned long long)hc2.pairs, hc2.n_next);
         n_pend = hc2.n_next;
         uint32_t* t = pend; pend = next; next = t;
     }

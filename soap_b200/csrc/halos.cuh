@@ -111,6 +111,8 @@ struct DevCfg {
     RowLayout lay;
 };
 
+struct Cuts;  // moments.cuh
+
 // Per-halo arrays (inputs are caller memory, the rest is workspace).
 struct HaloArrays {
     const double* cofp;
@@ -140,7 +142,11 @@ struct HaloArrays {
     uint32_t* n_items;
     unsigned int* cursor;      // append cursor of single-bucket halos (k_collect)
     unsigned int* items_done;  // last-arriver counter (k_moments)
-    int32_t* mslot;            // global bank slot of multi-item halos, -1 otherwise
+    int32_t* mslot;            // global bank slot of multi-item halos, -1 otherwise (projected apertures)
+    // moment banks of every halo accepted this round (written by the moment kernels, read by k_rows)
+    double* gbank;
+    unsigned long long* bank_off;  // [H] offset of the halo's banks in gbank (doubles)
+    Cuts* cuts;                    // [H] shell cuts of the selections committed this round
     // ladder look-ahead: one count sweep bins the sphere of the furthest rung by rung
     int32_t* look;             // rungs covered by this round's sweep (1..LOOK_MAX)
     uint32_t* rung_cnt;        // [H][LOOK_MAX] particles first included at rung k
@@ -165,7 +171,7 @@ struct Counters {
     unsigned int n_try, n_big, n_acc, n_next, n_multi, n_fine;
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
-    unsigned int n_mslot, items_overflow;
+    unsigned int n_mslot, items_overflow, n_bslot, n_seq;
     unsigned long long pairs, candidates, count_pairs, mom_pairs;
 };
 

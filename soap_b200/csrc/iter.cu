@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(TB, 3) k_it_accum(ChunkView v, HaloArrays ha, 
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.cur_r[h];
         const double halfL = 0.5 * v.L, L = v.L;
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             double r2 = 0.0, x = 0.0, y = 0.0, z = 0.0, m = 0.0, nrm = 1.0;
             uint32_t tbit = 0;

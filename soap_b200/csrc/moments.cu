@@ -30,7 +30,7 @@ template <int V, int NTY>
 __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(ChunkView v, HaloArrays ha, DevCfg cfg,
                                                 const Item* __restrict__ items,
                                                 const unsigned int* __restrict__ n_items_dev,
-                                                double* __restrict__ gbanks, int gbank_stride, int priv) {
+                                                int gbank_stride, int priv) {
     // dynamic shared memory: [priv ? NW : 1][gbank_stride] banks, then the
     // per-warp staging tiles [NW][32][VP] and their keys [NW][32]
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
     double* bank_w = banks + (priv ? (size_t)wid * gbank_stride : 0);
     __shared__ SweepShared SW;
     __shared__ Cuts cuts;
-    __shared__ int s_last;
     const unsigned int n_items = *n_items_dev;
     for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const Item im = items[it];
@@ -51,16 +50,18 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         // properties [lo, hi) of halo_prop_list were computed at this rung
         const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
         if (c_hi <= c_lo || ha.status[h] >= 2) continue;
-        const bool sub_c = cfg.do_sub && c_lo == 0;
         const ScanRes* sr = ha.sres + h;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.rung_r[h];
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         const bool central = ha.central[h] == 1;
         const int n_so = central ? cfg.n_so : 0;
         __syncthreads();
-        if (threadIdx.x == 32) build_cuts(cuts, cfg, sr, c_lo, c_hi, n_so);
+        if (threadIdx.x == 32) {
+            build_cuts(cuts, cfg, sr, c_lo, c_hi, n_so);
+            if (im.k == 0) ha.cuts[h] = cuts;  // for k_rows
+        }
         __syncthreads();
         const int ncut = cuts.n;
         const int nbank = (ncut + 1) * 2 * NTY;
@@ -103,25 +104,41 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
             }
             __syncthreads();
         }
-        // halos swept by several work items: combine in global banks; the last
-        // item to arrive writes the result row
-        const uint32_t n_it = ha.n_items[h];
-        if (n_it > 1) {
-            double* gb = gbanks + (size_t)ha.mslot[h] * gbank_stride;
-            for (int i = threadIdx.x; i < nbank * V; i += TB)
-                if (banks[i] != 0.0) atomicAdd(&gb[i], banks[i]);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) s_last = (atomicAdd(&ha.items_done[h], 1u) == n_it - 1) ? 1 : 0;
-            __syncthreads();
-            if (!s_last) continue;
-            __threadfence();
-            for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = __ldcg(&gb[i]);
-            __syncthreads();
+        // the halo's banks go to global memory (several work items of one halo add theirs up);
+        // k_rows turns them into the result row
+        {
+            double* gb = ha.gbank + ha.bank_off[h];
+            if (ha.n_items[h] > 1) {
+                for (int i = threadIdx.x; i < nbank * V; i += TB)
+                    if (banks[i] != 0.0) atomicAdd(&gb[i], banks[i]);
+            } else {
+                for (int i = threadIdx.x; i < nbank * V; i += TB) gb[i] = banks[i];
+            }
         }
-        write_row<V, NTY>(banks, cuts, ncut, cfg, ha, h, sr, sub_c, n_so, cx, cy, cz, (int)threadIdx.x);
         __syncthreads();
     }
+}
+
+// Result rows: one thread per (halo, selection) -- BoundSubhalo, each SO, each aperture.  The
+// selections of a warp are the same, so the row writer's branches do not diverge.
+struct SelIds {
+    int n;
+    int id[1 + SOAP_MAX_SO + SOAP_MAX_APERTURES];
+};
+template <int V, int NTY>
+__global__ void __launch_bounds__(128) k_rows(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ list,
+                                              const unsigned int* __restrict__ n_list, SelIds sels) {
+    const unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= *n_list) return;
+    const uint32_t h = list[it];
+    const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+    if (c_hi <= c_lo || ha.status[h] >= 2) return;
+    const int sel = sels.id[blockIdx.y];
+    const bool central = ha.central[h] == 1;
+    const int n_so = central ? cfg.n_so : 0;
+    const Cuts& cuts = ha.cuts[h];
+    write_row<V, NTY>(ha.gbank + ha.bank_off[h], cuts, cuts.n, cfg, ha, h, ha.sres + h, cfg.do_sub && c_lo == 0, n_so,
+                      ha.cofp[3 * h], ha.cofp[3 * h + 1], ha.cofp[3 * h + 2], sel);
 }
 
 __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, Dev
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.rung_r[h];
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         __syncthreads();
         if (threadIdx.x == 0) nsel = kappa_build_sels(sel, cfg, ha, h, c_lo, c_hi);
         for (int i = threadIdx.x; i < (1 + SOAP_MAX_APERTURES) * 11; i += TB) (&acc[0][0])[i] = 0.0;
@@ -188,9 +205,34 @@ __global__ void k_write_input_cols(HaloArrays ha, int64_t nh) {
 
 }  // namespace
 
+int soap_bank_stride(const DevCfg& cfg) {
+    const bool full = (cfg.flags & (PF_KIN | PF_KAPPA | PF_TENS)) != 0;
+    return (cfg.n_so + cfg.n_ap + 3) * 2 * (cfg.dmo ? 1 : 4) * (full ? V_FULL : V_MIN);
+}
+
+// result rows of the halos of `list` from their global banks (ha.gbank / ha.bank_off / ha.cuts)
+int soap_launch_rows(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
+                     const unsigned int* n_list_dev, unsigned int n_list_host, cudaStream_t stream) {
+    soap_handle* h = c->h;
+    if (n_list_host == 0) return 0;
+    const bool full = (cfg.flags & (PF_KIN | PF_KAPPA | PF_TENS)) != 0;
+    SelIds sels;
+    sels.n = 0;
+    if (cfg.do_sub) sels.id[sels.n++] = 0;
+    for (int q = 0; q < cfg.n_so; q++) sels.id[sels.n++] = 1 + q;
+    for (int a = 0; a < cfg.n_ap; a++) sels.id[sels.n++] = 1 + SOAP_MAX_SO + a;
+    if (sels.n == 0) return 0;
+    const dim3 grid(grid_for(n_list_host, 128), (unsigned)sels.n);
+    if (full && !cfg.dmo) LAUNCH(h, (k_rows<V_FULL, 4>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);
+    else if (full) LAUNCH(h, (k_rows<V_FULL, 1>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);
+    else if (!cfg.dmo) LAUNCH(h, (k_rows<V_MIN, 4>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);
+    else LAUNCH(h, (k_rows<V_MIN, 1>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);
+    return 0;
+}
+
 int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
-                        const unsigned int* n_items_dev, unsigned int n_items_host,
-                        unsigned int n_mslot, unsigned int grid, cudaStream_t stream) {
+                        const unsigned int* n_items_dev, unsigned int n_items_host, unsigned int grid,
+                        cudaStream_t stream) {
     soap_handle* h = c->h;
     const bool full = (cfg.flags & (PF_KIN | PF_KAPPA | PF_TENS)) != 0;
     const int nty = cfg.dmo ? 1 : 4;
@@ -202,17 +244,13 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     const int priv = ((size_t)NW * stride * sizeof(double) + stage_bytes <= 96 * 1024) ? 1 : 0;
     const size_t smem = (size_t)(priv ? NW : 1) * stride * sizeof(double) + stage_bytes;
     if (smem > 220 * 1024) SOAP_FAIL("soap_process_halos: %d SO + %d aperture variations need %zu bytes of shared memory", cfg.n_so, cfg.n_ap, smem);
-    double* gbanks = (double*)h->get("h_gbanks", sizeof(double) * (size_t)stride * (n_mslot + 1));
-    if (!gbanks) return -1;
-    if (n_mslot > 0) CUDA_TRY(cudaMemsetAsync(gbanks, 0, sizeof(double) * (size_t)stride * n_mslot, stream));
     unsigned int g = n_items_host < grid ? n_items_host : grid;
     if (g < 1) g = 1;
 #define MOM(VV, NT)                                                                                   \
     do {                                                                                              \
         CUDA_TRY(cudaFuncSetAttribute(k_moments<VV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)smem));                                                    \
-        LAUNCH(h, (k_moments<VV, NT>), g, TB, smem, stream, c->v, ha, cfg, items, n_items_dev, gbanks, \
-               stride, priv);                                                                         \
+        LAUNCH(h, (k_moments<VV, NT>), g, TB, smem, stream, c->v, ha, cfg, items, n_items_dev, stride, priv); \
     } while (0)
     if (full && nty == 4) MOM(V_FULL, 4);
     else if (full) MOM(V_FULL, 1);
@@ -233,6 +271,13 @@ int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, co
     if (g < 1) g = 1;
     LAUNCH(h, k_kappa, g, TB, 0, stream, c->v, ha, cfg, items, n_items_dev);
     LAUNCH(h, k_kappa_finish, grid_for(n_acc_host, 128), 128, 0, stream, ha, cfg, acc_list, n_acc_dev);
+    return 0;
+}
+
+int soap_launch_kappa_finish(soap_handle* h, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
+                             const unsigned int* n_list_dev, unsigned int n_list_host, cudaStream_t stream) {
+    if (n_list_host == 0) return 0;
+    LAUNCH(h, k_kappa_finish, grid_for(n_list_host, 128), 128, 0, stream, ha, cfg, list, n_list_dev);
     return 0;
 }
 

@@ -177,7 +177,7 @@ __device__ inline void build_cuts(Cuts& c, const DevCfg& cfg, const ScanRes* sr,
 template <int V, int NTY>
 __device__ __forceinline__ int moment_terms(const Cuts& cuts, int ncut, const DevCfg& cfg, double x, double y,
                                             double z, double r, double m, double vx, double vy, double vz,
-                                            int32_t g, int32_t hidx, int32_t fof, int32_t cen_fof, uint32_t tc,
+                                            int32_t g, int64_t hidx, int32_t fof, int32_t cen_fof, uint32_t tc,
                                             double (&val)[V]) {
                     int shell = 0;
                     for (int k = 0; k < ncut; k++) shell += cuts.strict[k] ? !(r < cuts.r[k]) : !(r <= cuts.r[k]);

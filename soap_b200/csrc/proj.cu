@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(TB) k_projected(ChunkView v, HaloArrays ha, De
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
         const double R = ha.rung_r[h];
         const double r2max = __dmul_rn(R, R), halfL = 0.5 * v.L, L = v.L;
-        const int32_t hidx = (int32_t)ha.index[h];
+        const int64_t hidx = ha.index[h];
         __syncthreads();
         for (int w = 0; w < (priv ? NW : 1); w++)
             for (int i = threadIdx.x; i < nbank * PV; i += TB) banks[(size_t)w * stride + i] = 0.0;
@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(TB) k_projected(ChunkView v, HaloArrays ha, De
                 if (banks[i] != 0.0) atomicAdd(&gb[i], banks[i]);
             __threadfence();
             __syncthreads();
-            // the moment stage used items_done up to n_it; this stage counts on from there
-            if (threadIdx.x == 0) s_last = (atomicAdd(&ha.items_done[h], 1u) == 2 * n_it - 1) ? 1 : 0;
+            if (threadIdx.x == 0) s_last = (atomicAdd(&ha.items_done[h], 1u) == n_it - 1) ? 1 : 0;
             __syncthreads();
             if (!s_last) continue;
             __threadfence();

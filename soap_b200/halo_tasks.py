@@ -51,6 +51,8 @@ class HaloPropConfig:
     projected: List[tuple] = field(default_factory=list)
     property_flags: int = 0
     dmo: bool = False
+    # cross-check switch (bit 0: every halo through the general kernel-sequence path); 0 in production
+    debug_flags: int = 0
 
     def so_reference_density(self, i):
         """SO_properties.py:3494-3512."""
@@ -115,6 +117,11 @@ class HaloPropConfig:
             c.proj_physical_mpc[i] = float(mpc)
         c.property_flags = int(self.property_flags)
         c.dmo = int(self.dmo)
+        c.n_filters = 0
+        for i in range(_lib.SOAP_MAX_APERTURES):
+            c.ap_prev_radius[i] = -1.0
+            c.proj_prev_radius[i] = -1.0
+        c.debug_flags = int(self.debug_flags)
         return c
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_lib_loads_and_reports_version():
     L = _lib.lib()
-    assert L.soap_abi_version() == 1
+    assert L.soap_abi_version() == _lib.ABI_VERSION
 
 
 def test_layout_is_pure_host_logic():

@@ -1,9 +1,7 @@
 """Full-size checks of the CUDA path on BASELINE config 2 (512^3 particles, 2e5
 halos) through properties that need no oracle run, plus the cross-check that
-the three execution tiers (fused warp tiers, fused CTA tier, general path)
+the staged small-halo tiers (tier.cu) and the general kernel-sequence path
 implement one semantics."""
-
-import os
 
 import numpy as np
 import pytest
@@ -19,18 +17,17 @@ SO4 = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.v
 def _process(data, halos, cp, L, no_tiers=False, fine_ppc=0, cfg=None):
     from soap_b200.halo_tasks import DeviceChunk, process_halos
 
+    import dataclasses
+
     cfg = cfg or cmp.device_config(cp, so=SO4, flags=8, dmo=True)
-    if no_tiers:
-        os.environ["SOAP_B200_NO_TIERS"] = "1"
-    try:
-        chunk = DeviceChunk(data, L, fine_ppc=fine_ppc)
-        res = process_halos(chunk, cfg, halos)
-        out = {n: res.get(n).copy() for n in res.names()}
-        st = res.status.cpu().numpy()
-        pairs = chunk.last_pairs()
-        chunk.free()
-    finally:
-        os.environ.pop("SOAP_B200_NO_TIERS", None)
+    # debug_flags bit 0: every halo through the general kernel-sequence path (include/soap_b200.h)
+    cfg = dataclasses.replace(cfg, debug_flags=1 if no_tiers else 0)
+    chunk = DeviceChunk(data, L, fine_ppc=fine_ppc)
+    res = process_halos(chunk, cfg, halos)
+    out = {n: res.get(n).copy() for n in res.names()}
+    st = res.status.cpu().numpy()
+    pairs = chunk.last_pairs()
+    chunk.free()
     return out, st, pairs
 
 
