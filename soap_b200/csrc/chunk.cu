@@ -20,7 +20,7 @@ constexpr int TB = 256;
 
 struct Geom {
     double pmin[3], cs[3];
-    int res;
+    int res, nb;
 };
 
 __global__ void __launch_bounds__(TB) k_cell_keys(const double* __restrict__ pos, int64_t n, Geom g,
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(TB) k_cell_keys(const double* __restrict__ pos
     int cx = cell_coord(pos[3 * i], g.pmin[0], g.cs[0], g.res);
     int cy = cell_coord(pos[3 * i + 1], g.pmin[1], g.cs[1], g.res);
     int cz = cell_coord(pos[3 * i + 2], g.pmin[2], g.cs[2], g.res);
-    key[i] = (uint32_t)cx + (uint32_t)g.res * ((uint32_t)cy + (uint32_t)g.res * (uint32_t)cz);
+    key[i] = blocked_cell(cx, cy, cz, g.nb);
     val[i] = base + (uint32_t)i;
 }
 
@@ -65,11 +65,12 @@ struct SoAOut {
     float *mass, *vx, *vy, *vz;
     int32_t *grnr, *fof;
     uint8_t* type;
-    uint32_t* orig;
 };
 
 // cell-ordered SoA: slot d takes particle perm[d] (coalesced writes, gathered reads)
-__global__ void __launch_bounds__(TB) k_gather(TypesIn in, const uint32_t* __restrict__ perm, uint32_t n, SoAOut o) {
+// ids_bad is set when a 64-bit group id does not fit the 32 bits kept on the device
+__global__ void __launch_bounds__(TB) k_gather(TypesIn in, const uint32_t* __restrict__ perm, uint32_t n, SoAOut o,
+                                               int* __restrict__ ids_bad) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n) return;
     const uint32_t src = perm[d];
@@ -87,14 +88,15 @@ __global__ void __launch_bounds__(TB) k_gather(TypesIn in, const uint32_t* __res
     o.vy[d] = T.vel[3 * (size_t)i + 1];
     o.vz[d] = T.vel[3 * (size_t)i + 2];
     if (T.id64) {
-        o.grnr[d] = (int32_t)((const int64_t*)T.grnr)[i];
-        o.fof[d] = (int32_t)((const int64_t*)T.fof)[i];
+        const int64_t g64 = ((const int64_t*)T.grnr)[i], f64 = ((const int64_t*)T.fof)[i];
+        if (g64 != (int64_t)(int32_t)g64 || f64 != (int64_t)(int32_t)f64) *ids_bad = 1;
+        o.grnr[d] = (int32_t)g64;
+        o.fof[d] = (int32_t)f64;
     } else {
         o.grnr[d] = ((const int32_t*)T.grnr)[i];
         o.fof[d] = ((const int32_t*)T.fof)[i];
     }
     o.type[d] = T.tcode;
-    o.orig[d] = i;
 }
 
 template <typename T>
@@ -152,13 +154,15 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     v.n = n;
     v.L = boxsize;
     v.res = res;
+    const int nb = (res + BLK - 1) / BLK;
+    v.nb = nb;
     for (int d = 0; d < 3; d++) {
         if (pmin[d] == pmax[d]) pmax[d] = pmin[d] + 1.0;
         v.pmin[d] = pmin[d];
         v.pmax[d] = pmax[d];
         v.cs[d] = (pmax[d] - pmin[d]) / res;
     }
-    const int64_t ncell = (int64_t)res * res * res;
+    const int64_t ncell = (int64_t)nb * nb * nb * BLK_CELLS;  // blocked cell ids (ids of cells beyond res stay empty)
     SoAOut o;
     uint32_t* cell_off = nullptr;
     int rc = 0;
@@ -167,7 +171,7 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     rc |= dev_alloc(c, &o.mass, n);
     rc |= dev_alloc(c, &o.vx, n); rc |= dev_alloc(c, &o.vy, n); rc |= dev_alloc(c, &o.vz, n);
     rc |= dev_alloc(c, &o.grnr, n); rc |= dev_alloc(c, &o.fof, n);
-    rc |= dev_alloc(c, &o.type, n); rc |= dev_alloc(c, &o.orig, n);
+    rc |= dev_alloc(c, &o.type, n);
     if (rc) { soap_chunk_destroy(c); return -1; }
     uint32_t* key = (uint32_t*)h->get("chunk_key", sizeof(uint32_t) * (size_t)n);
     uint32_t* val = (uint32_t*)h->get("chunk_val", sizeof(uint32_t) * (size_t)n);
@@ -179,6 +183,7 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     Geom g;
     for (int d = 0; d < 3; d++) { g.pmin[d] = v.pmin[d]; g.cs[d] = v.cs[d]; }
     g.res = res;
+    g.nb = nb;
 #define CK(stmt) do { if ((stmt) != 0) { soap_chunk_destroy(c); return -1; } } while (0)
 #define CKL(...) do { auto _f = [&]() -> int { __VA_ARGS__; return 0; }; if (_f() != 0) { soap_chunk_destroy(c); return -1; } } while (0)
     c->create_log.begin("mesh_keys", stream);
@@ -207,7 +212,12 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     CKL(LAUNCH(h, k_cell_offsets, grid_for(n + 1, TB), TB, 0, stream, key, (uint32_t)n, (uint32_t)ncell, cell_off));
     c->create_log.end(stream);
     c->create_log.begin("reorder", stream);
-    CKL(LAUNCH(h, k_gather, grid_for(n, TB), TB, 0, stream, tin, val, (uint32_t)n, o));
+    int* ids_bad = (int*)h->get("chunk_ids_bad", sizeof(int));
+    if (!ids_bad) { soap_chunk_destroy(c); return -1; }
+    CK(cudaMemsetAsync(ids_bad, 0, sizeof(int), stream) != cudaSuccess);
+    CKL(LAUNCH(h, k_gather, grid_for(n, TB), TB, 0, stream, tin, val, (uint32_t)n, o, ids_bad));
+    int ids_bad_host = 0;
+    CK(cudaMemcpyAsync(&ids_bad_host, ids_bad, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess);
     c->create_log.end(stream);
 #undef CK
 #undef CKL
@@ -215,7 +225,6 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     v.px = o.px; v.py = o.py; v.pz = o.pz;
     v.mass = o.mass; v.vx = o.vx; v.vy = o.vy; v.vz = o.vz;
     v.grnr = o.grnr; v.fof = o.fof; v.type = o.type;
-    c->orig = o.orig;
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) {
         snprintf(g_soap_err, sizeof(g_soap_err), "soap_chunk_create: %s", cudaGetErrorString(e));
@@ -223,6 +232,14 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
         return -1;
     }
     c->create_log.collect();
+    if (ids_bad_host) {
+        // membership is an integer-exact contract: ids that differ by a multiple of 2^32 must not alias
+        snprintf(g_soap_err, sizeof(g_soap_err),
+                 "soap_chunk_create: a GroupNr_bound / FOFGroupIDs value does not fit in 32 bits (the device keeps "
+                 "group ids as int32; re-index the groups of this chunk)");
+        soap_chunk_destroy(c);
+        return -1;
+    }
     *out = c;
     return 0;
 }

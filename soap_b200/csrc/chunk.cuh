@@ -7,15 +7,28 @@ __host__ __device__ inline int ptype_code(int ptype) {
     return ptype == 0 ? 0 : (ptype == 1 ? 1 : (ptype == 4 ? 2 : 3));
 }
 
-// Device view of the chunk: all particle types merged, SoA, in the cell order
-// of an internal fine mesh (cell id = i + res*j + res^2*k, so a run of cells
-// along i is one contiguous particle span).
+// Cells of the internal mesh are numbered block by block: blocks of 8 x 8 x 8 cells in (x, y, z)
+// order, cells inside a block in (x, y, z) order.  A run of cells along x inside one block is one
+// contiguous particle span, and the particles of a block (a few thousand, ~200 KB of payload) sit
+// together in memory: the reorder pass reads the input, which arrives in SWIFT top-level cell order
+// (swift_cells.py:551-737), one slab at a time out of L2 instead of striding across the whole
+// z-plane, and a sphere's rows in neighbouring y / z are neighbours in memory too.
+constexpr int BLK = 8, BLK_SHIFT = 3, BLK_CELLS = BLK * BLK * BLK;
+__host__ __device__ inline uint32_t blocked_cell(int i, int j, int k, int nb) {
+    return (((uint32_t)(k >> BLK_SHIFT) * (uint32_t)nb + (uint32_t)(j >> BLK_SHIFT)) * (uint32_t)nb +
+            (uint32_t)(i >> BLK_SHIFT)) * (uint32_t)BLK_CELLS +
+           (uint32_t)((((k & (BLK - 1)) << BLK_SHIFT) + (j & (BLK - 1))) << BLK_SHIFT) + (uint32_t)(i & (BLK - 1));
+}
+
+// Device view of the chunk: all particle types merged, SoA, in the blocked cell order
+// of an internal fine mesh.
 struct ChunkView {
     int64_t n;
     double L;
     int res;
+    int nb;  // blocks per dimension = ceil(res / BLK)
     double pmin[3], pmax[3], cs[3];
-    const uint32_t* cell_off;  // [res^3 + 1]
+    const uint32_t* cell_off;  // [nb^3 * BLK_CELLS + 1], indexed by blocked_cell()
     const double *px, *py, *pz;
     const float *mass, *vx, *vy, *vz;
     const int32_t *grnr, *fof;
@@ -61,7 +74,6 @@ struct soap_chunk {
     cudaStream_t stream = nullptr;
     ChunkView v{};
     std::vector<void*> owned;  // device allocations freed at destroy
-    uint32_t* orig = nullptr;  // [n] index within the particle's own ptype array
     int64_t last_pairs = 0;
     int64_t last_small_pairs = 0;  // of which handled by the fused small-halo tiers
     int64_t last_tier_pairs[3] = {0, 0, 0};

@@ -139,84 +139,102 @@ __global__ void k_tier_place(HaloArrays ha, int64_t nh, uint32_t* list0, uint32_
 }
 
 // ------------------------------------------------------------- k_plan_items
-// One thread per pending halo: count the candidates of its rows at the current
-// radius and cut the candidate stream into work items of ITEM_CAND particles.
-__global__ void __launch_bounds__(128) k_plan_items(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
-                                                    const unsigned int* __restrict__ n_pend,
-                                                    Item* __restrict__ items, unsigned int items_cap,
-                                                    Counters* ctr, int look, int replan, int bank_stride) {
-    unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per pending halo: count the candidates of its rows at the current radius and cut the
+// candidate stream into work items of ITEM_CAND particles (lanes stride over the rows: the spheres
+// of ladder stragglers have tens of thousands of them).
+constexpr int PLAN_NT = 128;
+__global__ void __launch_bounds__(PLAN_NT) k_plan_items(ChunkView v, HaloArrays ha, const uint32_t* __restrict__ pend,
+                                                        const unsigned int* __restrict__ n_pend,
+                                                        Item* __restrict__ items, unsigned int items_cap,
+                                                        Counters* ctr, int look, int replan, int bank_stride) {
+    __shared__ DimRanges rg_s[PLAN_NT / 32][3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int it = blockIdx.x * (PLAN_NT / 32) + wid;
     if (it >= *n_pend) return;
     const uint32_t h = pend[it];
-    DimRanges rg[3];
+    DimRanges* rg = rg_s[wid];
     // round start: plan the sweep of the furthest of the next `look` ladder rungs;
     // replan: the sweep of the accepted rung (collect / moments)
     double r = ha.cur_r[h];
     if (!replan) {
         double rr[LOOK_MAX];
         const int nr = ladder_radii(r, ha.rr_in[h], look, rr);
-        ha.look[h] = nr;
         r = rr[nr - 1];
-        for (int k = 0; k < LOOK_MAX; k++) { ha.rung_cnt[(size_t)h * LOOK_MAX + k] = 0; ha.rung_msum[(size_t)h * LOOK_MAX + k] = 0.0; }
+        if (lane == 0) ha.look[h] = nr;
+        if (lane < LOOK_MAX) { ha.rung_cnt[(size_t)h * LOOK_MAX + lane] = 0; ha.rung_msum[(size_t)h * LOOK_MAX + lane] = 0.0; }
     }
-    for (int d = 0; d < 3; d++)
-        dim_ranges(ha.cofp[3 * h + d], r, v.L, v.pmin[d], v.pmax[d], v.cs[d], v.res, rg[d]);
+    if (lane < 3) dim_ranges(ha.cofp[3 * h + lane], r, v.L, v.pmin[lane], v.pmax[lane], v.cs[lane], v.res, rg[lane]);
+    __syncwarp();
     const RowIter ri = row_iter(rg);
     unsigned long long cand = 0;
-    for (int row = 0; row < ri.nrows; row++) {
+    for (int row = lane; row < ri.nrows; row += 32) {
         uint32_t s0, s1;
         row_span(v, rg, ri, row, s0, s1);
         cand += s1 - s0;
     }
+    cand = warp_sum_u64(cand);
     if (cand > 0xfffffff0ull) cand = 0xfffffff0ull;
     uint32_t ni = (uint32_t)((cand + ITEM_CAND - 1) / ITEM_CAND);
     if (ni < 1) ni = 1;
-    uint32_t base = atomicAdd(&ctr->n_items, ni);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->n_items, ni);
+    base = __shfl_sync(0xffffffffu, base, 0);
     if (base + ni > items_cap) {
         // the host grows the item list to n_items and plans this rung again
-        atomicExch(&ctr->items_overflow, 1u);
+        if (lane == 0) atomicExch(&ctr->items_overflow, 1u);
         return;
     }
-    ha.item_base[h] = base;
-    ha.n_items[h] = ni;
-    ha.cursor[h] = 0;
-    ha.items_done[h] = 0;
-    if (!replan) {
-        ha.cnt[h] = 0;
-        ha.msum[h] = 0.0;
-        ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
-    }
-    ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
-    if (replan) ha.bank_off[h] = (unsigned long long)atomicAdd(&ctr->n_bslot, 1u) * (unsigned long long)bank_stride;
-    if (ni == 1) {
-        Item im;
-        im.halo = h; im.first = 0; im.count = (uint32_t)cand; im.row0 = 0;
-        im.pos0 = 0; im.k = 0; im.pad0 = im.pad1 = 0;
-        items[base] = im;
-    } else {
-        // second walk: the row in which each item's range starts
-        unsigned long long pos = 0;
-        uint32_t k = 0;
-        for (int row = 0; row < ri.nrows && k < ni; row++) {
-            uint32_t s0, s1;
-            row_span(v, rg, ri, row, s0, s1);
-            const unsigned long long end = pos + (s1 - s0);
-            while (k < ni && (unsigned long long)k * ITEM_CAND < end) {
-                Item im;
-                im.halo = h;
-                im.first = k * ITEM_CAND;
-                const unsigned long long left = cand - (unsigned long long)k * ITEM_CAND;
-                im.count = (uint32_t)(left < ITEM_CAND ? left : ITEM_CAND);
-                im.row0 = (uint32_t)row;
-                im.pos0 = (uint32_t)pos;
-                im.k = k; im.pad0 = im.pad1 = 0;
-                items[base + k] = im;
-                k++;
-            }
-            pos = end;
+    if (lane == 0) {
+        ha.item_base[h] = base;
+        ha.n_items[h] = ni;
+        ha.cursor[h] = 0;
+        ha.items_done[h] = 0;
+        if (!replan) {
+            ha.cnt[h] = 0;
+            ha.msum[h] = 0.0;
+            ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
+            atomicAdd(&ctr->candidates, cand);
+        }
+        ha.mslot[h] = ni > 1 ? (int32_t)atomicAdd(&ctr->n_mslot, 1u) : -1;
+        if (replan) ha.bank_off[h] = (unsigned long long)atomicAdd(&ctr->n_bslot, 1u) * (unsigned long long)bank_stride;
+        if (ni == 1) {
+            Item im;
+            im.halo = h; im.first = 0; im.count = (uint32_t)cand; im.row0 = 0;
+            im.pos0 = 0; im.k = 0; im.pad0 = im.pad1 = 0;
+            items[base] = im;
         }
     }
-    if (!replan) atomicAdd(&ctr->candidates, cand);
+    if (ni > 1) {
+        // second walk: item k starts in the row that holds candidate k * ITEM_CAND of the stream
+        unsigned long long pos = 0;
+        for (int row0 = 0; row0 < ri.nrows; row0 += 32) {
+            const int row = row0 + lane;
+            uint32_t s0 = 0, s1 = 0;
+            if (row < ri.nrows) row_span(v, rg, ri, row, s0, s1);
+            const unsigned long long len = s1 - s0;
+            unsigned long long incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned long long end = pos + incl, start = end - len;
+            if (len > 0) {
+                for (unsigned long long k = (start + ITEM_CAND - 1) / ITEM_CAND; k < ni && k * ITEM_CAND < end; k++) {
+                    Item im;
+                    im.halo = h;
+                    im.first = (uint32_t)(k * ITEM_CAND);
+                    const unsigned long long left = cand - k * ITEM_CAND;
+                    im.count = (uint32_t)(left < ITEM_CAND ? left : ITEM_CAND);
+                    im.row0 = (uint32_t)row;
+                    im.pos0 = (uint32_t)start;
+                    im.k = (uint32_t)k; im.pad0 = im.pad1 = 0;
+                    items[base + k] = im;
+                }
+            }
+            pos += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
 }
 
 // ----------------------------------------------------------------- k_count
@@ -1036,7 +1054,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     auto plan = [&](const uint32_t* list, const unsigned int* n_dev, unsigned int n_host, int look, int replan) -> int {
         for (int attempt = 0; attempt < 2; attempt++) {
             CUDA_TRY(cudaMemsetAsync(&ctr->n_items, 0, 4 * sizeof(unsigned int), stream));  // n_items, n_mslot, items_overflow, n_bslot
-            LAUNCH(h, k_plan_items, grid_for(n_host, 128), 128, 0, stream, v, ha, list, n_dev, items,
+            LAUNCH(h, k_plan_items, grid_for(n_host, PLAN_NT / 32), PLAN_NT, 0, stream, v, ha, list, n_dev, items,
                    (unsigned int)items_cap, ctr, look, replan, bank_stride);
             Counters pc;
             CUDA_TRY(cudaMemcpyAsync(&pc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));

@@ -224,27 +224,45 @@ __device__ __forceinline__ int range_cell(const DimRanges& r, int idx) {
     return r.lo[0];
 }
 
-// Row = one run of cells along x for fixed (y, z): a contiguous particle span.
+// Row = one run of cells along x inside one block, for fixed (y, z): a contiguous particle span.
+// nx = number of such pieces over the x ranges of the sphere.
 struct RowIter {
     int ny, nx, nrows;
 };
+__device__ __forceinline__ int range_pieces(const DimRanges& r) {
+    int t = 0;
+    for (int a = 0; a < r.n; a++) t += (r.hi[a] >> BLK_SHIFT) - (r.lo[a] >> BLK_SHIFT) + 1;
+    return t;
+}
 __device__ __forceinline__ RowIter row_iter(const DimRanges* rg) {
     RowIter it;
     it.ny = range_total(rg[1]);
-    it.nx = rg[0].n;
+    it.nx = range_pieces(rg[0]);
     it.nrows = range_total(rg[2]) * it.ny * it.nx;
     return it;
 }
 __device__ __forceinline__ void row_span(const ChunkView& v, const DimRanges* rg, const RowIter& it,
                                          int row, uint32_t& s0, uint32_t& s1) {
-    int rx = row % it.nx;
+    int px = row % it.nx;
     int t = row / it.nx;
     int jy = range_cell(rg[1], t % it.ny);
     int kz = range_cell(rg[2], t / it.ny);
-    uint32_t c0 = (uint32_t)rg[0].lo[rx] + (uint32_t)v.res * ((uint32_t)jy + (uint32_t)v.res * (uint32_t)kz);
-    uint32_t c1 = c0 + (uint32_t)(rg[0].hi[rx] - rg[0].lo[rx]);
+    // piece px of the x ranges: cells [x0, x1] of one block
+    int x0 = rg[0].lo[0], x1 = rg[0].hi[0];
+    for (int a = 0; a < rg[0].n; a++) {
+        const int lo = rg[0].lo[a], hi = rg[0].hi[a];
+        const int np = (hi >> BLK_SHIFT) - (lo >> BLK_SHIFT) + 1;
+        if (px < np || a == rg[0].n - 1) {
+            const int b0 = ((lo >> BLK_SHIFT) + px) << BLK_SHIFT;
+            x0 = b0 > lo ? b0 : lo;
+            x1 = b0 + BLK - 1 < hi ? b0 + BLK - 1 : hi;
+            break;
+        }
+        px -= np;
+    }
+    const uint32_t c0 = blocked_cell(x0, jy, kz, v.nb);
     s0 = v.cell_off[c0];
-    s1 = v.cell_off[c1 + 1];
+    s1 = v.cell_off[c0 + (uint32_t)(x1 - x0) + 1u];
 }
 __device__ __forceinline__ void halo_ranges(const ChunkView& v, double cx, double cy, double cz,
                                             double r, DimRanges* rg, int d) {

@@ -27,27 +27,28 @@ static __global__ void __launch_bounds__(RS_TB) k_rs_hist(const uint32_t* __rest
     ghist[(size_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];  // digit-major: one scan gives global offsets
 }
 
-static __global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __restrict__ key_in,
-                                                      const uint32_t* __restrict__ val_in, uint32_t n, int shift,
-                                                      uint32_t nblk, const uint32_t* __restrict__ goff,
-                                                      uint32_t* __restrict__ key_out,
-                                                      uint32_t* __restrict__ val_out) {
+static __global__ void __launch_bounds__(RS_TB, 4) k_rs_scatter(const uint32_t* __restrict__ key_in,
+                                                         const uint32_t* __restrict__ val_in, uint32_t n, int shift,
+                                                         uint32_t nblk, const uint32_t* __restrict__ goff,
+                                                         uint32_t* __restrict__ key_out,
+                                                         uint32_t* __restrict__ val_out) {
     constexpr int NW = RS_TB / 32;
     __shared__ uint32_t wcount[NW][RS_NB];  // running count of each digit within a warp's rows
     __shared__ uint32_t wbase[NW][RS_NB];   // exclusive prefix over the warps + the block's global offset
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NW * RS_NB; i += RS_TB) (&wcount[0][0])[i] = 0;
     __syncthreads();
-    // warp w owns the contiguous elements [w * 32 * IPT, (w + 1) * 32 * IPT) of the tile, row by row
+    // warp w owns the contiguous elements [w * 32 * IPT, (w + 1) * 32 * IPT) of the tile, row by row.
+    // Only the 16-bit ranks stay in registers across the barrier (two per register): keys and values
+    // are read again from L1 / L2 for the scatter, which keeps four CTAs resident per SM.
     const uint32_t wbeg = blockIdx.x * RS_TILE + wid * (32 * RS_IPT);
-    uint32_t k_[RS_IPT], v_[RS_IPT], rk[RS_IPT];
+    uint32_t rk2[RS_IPT / 2];
 #pragma unroll
     for (int r = 0; r < RS_IPT; r++) {
         const uint32_t i = wbeg + r * 32 + lane;
         const bool ok = i < n;
-        k_[r] = ok ? key_in[i] : 0xffffffffu;
-        v_[r] = ok ? val_in[i] : 0u;
-        const uint32_t d = ok ? ((k_[r] >> shift) & (RS_NB - 1)) : RS_NB;  // invalid lanes match each other only
+        const uint32_t k = ok ? key_in[i] : 0xffffffffu;
+        const uint32_t d = ok ? ((k >> shift) & (RS_NB - 1)) : RS_NB;  // invalid lanes match each other only
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -56,7 +57,8 @@ static __global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __r
             wcount[wid][d] = old + __popc(peers);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rk[r] = old + __popc(peers & ((1u << lane) - 1u));
+        const uint32_t rk = old + __popc(peers & ((1u << lane) - 1u));  // < 32 * RS_IPT
+        if (r & 1) rk2[r >> 1] |= rk << 16; else rk2[r >> 1] = rk;
         __syncwarp();
     }
     __syncthreads();
@@ -74,10 +76,11 @@ static __global__ void __launch_bounds__(RS_TB) k_rs_scatter(const uint32_t* __r
     for (int r = 0; r < RS_IPT; r++) {
         const uint32_t i = wbeg + r * 32 + lane;
         if (i < n) {
-            const uint32_t d = (k_[r] >> shift) & (RS_NB - 1);
-            const uint32_t dst = wbase[wid][d] + rk[r];
-            key_out[dst] = k_[r];
-            val_out[dst] = v_[r];
+            const uint32_t k = key_in[i], vv = val_in[i];
+            const uint32_t d = (k >> shift) & (RS_NB - 1);
+            const uint32_t dst = wbase[wid][d] + ((rk2[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
+            key_out[dst] = k;
+            val_out[dst] = vv;
         }
     }
 }

@@ -32,6 +32,17 @@ namespace {
 
 enum : int { ACT_TRY = 0, ACT_RETRY = 1, ACT_DONE = 2, ACT_OVERFLOW = 3 };
 
+// one gathered particle -> its record (halo-centred re-wrap, halo_tasks.py:106-117); kept out of line:
+// the unrolled sweep calls it from several sites and the kernel must stay small enough for the
+// instruction cache
+__device__ __noinline__ unsigned long long rel_radius_bits(double X, double Y, double Z, double cx, double cy,
+                                                           double cz, double L, double halfL) {
+    const double x = rewrap_rel(X, cx, L, halfL);
+    const double y = rewrap_rel(Y, cy, L, halfL);
+    const double z = rewrap_rel(Z, cz, L, halfL);
+    return (unsigned long long)__double_as_longlong(radius3(x, y, z));
+}
+
 template <int CAP>
 struct __align__(16) FrontSlot {
     Rec rec[CAP];
@@ -236,11 +247,8 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                 if (lane == 0) W.n_stage = base + __popc(bal);
                 if (isin) {
                     const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
-                    const double x = rewrap_rel(X[u], cx, L, halfL);
-                    const double y = rewrap_rel(Y[u], cy, L, halfL);
-                    const double z = rewrap_rel(Z[u], cz, L, halfL);
                     Rec rc;
-                    rc.rbits = (unsigned long long)__double_as_longlong(radius3(x, y, z));
+                    rc.rbits = rel_radius_bits(X[u], Y[u], Z[u], cx, cy, cz, L, halfL);
                     rc.m = v.mass[t];
                     const uint32_t tc = NCH == 2 ? 1u : (uint32_t)v.type[t];
                     rc.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u);
@@ -331,28 +339,21 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
         }
         if (!counted) {
             if (n <= 32) {
-                // one record per lane: bitonic network over shuffles
-                Rec mine;
+                // one record per lane: rank = number of records in front of mine (a short rolled loop;
+                // the unrolled shuffle network of the same job was a quarter of this kernel's code)
+                unsigned long long key = ~0ull;
                 uint32_t mp = 0xffffffffu;
-                if (lane < (int)n) { mine = W.rec[lane]; mp = W.pid[lane]; }
-                else { mine.rbits = ~0ull; mine.m = 0.f; mine.flags = 0; }
-#pragma unroll
-                for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        Rec o;
-                        o.rbits = __shfl_xor_sync(0xffffffffu, mine.rbits, j);
-                        o.m = __shfl_xor_sync(0xffffffffu, mine.m, j);
-                        o.flags = __shfl_xor_sync(0xffffffffu, mine.flags, j);
-                        const uint32_t op = __shfl_xor_sync(0xffffffffu, mp, j);
-                        const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
-                        const bool o_less = o.rbits < mine.rbits || (o.rbits == mine.rbits && op < mp);
-                        const bool m_less = mine.rbits < o.rbits || (mine.rbits == o.rbits && mp < op);
-                        if (take_min ? o_less : m_less) { mine = o; mp = op; }
-                    }
+                if (lane < (int)n) { key = W.rec[lane].rbits; mp = W.pid[lane]; }
+                uint32_t rank = 0;
+#pragma unroll 1
+                for (uint32_t j = 0; j < n; j++) {
+                    const unsigned long long kj = __shfl_sync(0xffffffffu, key, j);
+                    const uint32_t pj = __shfl_sync(0xffffffffu, mp, j);
+                    rank += (kj < key || (kj == key && pj < mp)) ? 1u : 0u;
                 }
+                if (lane < (int)n) W.ord[rank] = (uint16_t)lane;
                 __syncwarp();
-                if (lane < (int)n) { W.rec[lane] = mine; W.pid[lane] = mp; }
+                counted = true;  // W.ord is set
             } else {
                 uint32_t np2 = 64;
                 while (np2 < n) np2 <<= 1;
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                     }
                 }
             }
-            for (uint32_t i = lane; i < n; i += 32) W.ord[i] = (uint16_t)i;
+            if (!counted)
+                for (uint32_t i = lane; i < n; i += 32) W.ord[i] = (uint16_t)i;
             __syncwarp();
         }
         // ---------------------------------------------- hand over to the solve / moment kernels
