@@ -70,6 +70,21 @@ class Params:
     faithful: bool = True
     # also the iterative tensors (inertia_tensors.py default max_iterations = 20)
     iterative_tensors: bool = False
+    # CategoryFilter (category_filter.py:69-110): name -> (limit, particle types whose BoundSubhalo counts are summed)
+    filters: dict = field(default_factory=dict)
+
+
+N_KEY = {0: "Ngas", 1: "Ndm", 4: "Nstar", 5: "Nbh"}
+
+
+def do_calculation(params, halo_result, name):
+    """CategoryFilter.get_do_calculation (category_filter.py:69-110) for one category: "basic" is always
+    computed, the others need sum(BoundSubhalo/NumberOf*Particles) >= limit."""
+    if name == "basic":
+        return True
+    limit, types = params.filters[name]
+    sub = halo_result["BoundSubhalo"]  # KeyError like the reference if BoundSubhalo was not computed first
+    return sum(int(sub.get(N_KEY[t], 0)) for t in types) >= limit
 
 
 def _cast(arr, faithful):
@@ -165,8 +180,9 @@ def _tensor(mass, pos, R, params, reduced, search_radius=None, max_iterations=1)
 class SOOracle:
     """SOProperties (SO_properties.py:3215-3742) for the north-star keys."""
 
-    def __init__(self, params, SOval=200.0, type="crit", name=None):
+    def __init__(self, params, SOval=200.0, type="crit", name=None, halo_filter="basic"):
         self.params = params
+        self.halo_filter = halo_filter
         self.type = type
         self.mean_density_multiple = 1000.0  # SO_properties.py:3459-3462
         self.critical_density_multiple = 1000.0
@@ -196,7 +212,8 @@ class SOOracle:
     def calculate(self, input_halo, search_radius, data, halo_result):
         p = self.params
         res = {}
-        if not input_halo["is_central"]:  # SO_properties.py:3627
+        # SO_properties.py:3627: centrals only, and only if the halo passes this variation's filter
+        if not input_halo["is_central"] or not do_calculation(p, halo_result, self.halo_filter):
             halo_result[self.group_name] = res
             return
         centre = input_halo["cofp"]
@@ -486,8 +503,14 @@ class ApertureOracle:
     mean_density_multiple = None
     critical_density_multiple = None
 
-    def __init__(self, params, aperture_radius, physical_radius_mpc, inclusive, label):
+    def __init__(self, params, aperture_radius, physical_radius_mpc, inclusive, label, halo_filter="basic",
+                 prev_radius=None, prev_group=None):
         self.params = params
+        self.halo_filter = halo_filter
+        # all_radii_kpc[i_radius - 1] in coordinate units and the group of that aperture, or None when this is
+        # the first radius / the shortcut is off (compute_halo_properties.py:345-395)
+        self.prev_radius = prev_radius
+        self.prev_group = prev_group
         self.aperture_radius = aperture_radius  # coordinate units (unyt-converted)
         self.physical_radius_mpc = physical_radius_mpc
         self.inclusive = inclusive
@@ -496,6 +519,22 @@ class ApertureOracle:
 
     def calculate(self, input_halo, search_radius, data, halo_result):
         p = self.params
+        # aperture_properties.py:4082-4123: the previous aperture already held every bound particle ->
+        # inclusive: skipped (zeros); exclusive: the previous exclusive values are copied
+        do_calc = do_calculation(p, halo_result, self.halo_filter)
+        if self.prev_radius is not None and "EncloseRadius" in halo_result.get("BoundSubhalo", {}):
+            r_enclose = np.float32(halo_result["BoundSubhalo"]["EncloseRadius"])  # the stored output is float32
+            if self.prev_radius > r_enclose:
+                res = {}
+                if not self.inclusive and do_calc:
+                    res = dict(halo_result[self.prev_group])
+                halo_result[self.group_name] = res
+                return
+        # aperture_properties.py:4127: a halo that fails this variation's filter keeps its zeros and
+        # never asks for a larger radius
+        if not do_calc:
+            halo_result[self.group_name] = {}
+            return
         # aperture_properties.py:4140-4143
         if search_radius < self.aperture_radius:
             raise SearchRadiusTooSmallError("Search radius is smaller than aperture")
@@ -579,8 +618,12 @@ class ProjectedApertureOracle:
     mean_density_multiple = None
     critical_density_multiple = None
 
-    def __init__(self, params, aperture_radius, physical_radius_mpc, label):
+    def __init__(self, params, aperture_radius, physical_radius_mpc, label, halo_filter="basic", prev_radius=None,
+                 prev_group=None):
         self.params = params
+        self.halo_filter = halo_filter
+        self.prev_radius = prev_radius
+        self.prev_group = prev_group
         self.aperture_radius = aperture_radius
         self.physical_radius_mpc = physical_radius_mpc
         self.name = f"projected_aperture_{label}"
@@ -588,6 +631,18 @@ class ProjectedApertureOracle:
 
     def calculate(self, input_halo, search_radius, data, halo_result):
         p = self.params
+        # projected_aperture_properties.py:1826-1885: previous projected aperture held every bound particle ->
+        # its values are copied (whatever the filter says)
+        if self.prev_radius is not None and "EncloseRadius" in halo_result.get("BoundSubhalo", {}):
+            if self.prev_radius > np.float32(halo_result["BoundSubhalo"]["EncloseRadius"]):
+                for ax in "xyz":
+                    halo_result[f"{self.group_name}/proj{ax}"] = dict(halo_result[f"{self.prev_group}/proj{ax}"])
+                return
+        # projected_aperture_properties.py:1888
+        if not do_calculation(p, halo_result, self.halo_filter):
+            for ax in "xyz":
+                halo_result[f"{self.group_name}/proj{ax}"] = {}
+            return
         centre = input_halo["cofp"]
         index = input_halo["index"]
         mass, position, velocity, types = ([] for _ in range(4))

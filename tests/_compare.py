@@ -36,26 +36,47 @@ def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True, 
     )
 
 
-def oracle_prop_list(params, cp, so, apertures, do_subhalo=True, projected=()):
+def oracle_prop_list(params, cp, so, apertures, do_subhalo=True, projected=(), so_filters=None, ap_filters=None,
+                     proj_filters=None, skip_gt=()):
+    """halo_prop_list of the oracle; *_filters give the halo_filter category of each variation (in the order
+    of ``so`` / of the sorted apertures), default "basic".  skip_gt names the aperture kinds ("exclusive",
+    "inclusive", "projected") that know the radii of their siblings (all_radii_kpc, compute_halo_properties.py:
+    345-395; the reference always passes them to exclusive spheres) and so use the EncloseRadius shortcut."""
     props = []
     if do_subhalo:
         props.append(oh.SubhaloOracle(params))
-    for t, val in so:
-        props.append(oh.SOOracle(params, val, t))
-    aps = sorted(apertures, key=lambda a: (a[0], a[2]))
-    for i, (r, mpc, incl) in enumerate(aps):
-        props.append(oh.ApertureOracle(params, r, mpc, bool(incl), f"{i}"))
-    for i, (r, mpc) in enumerate(sorted(projected, key=lambda a: a[0])):
-        props.append(oh.ProjectedApertureOracle(params, r, mpc, f"{i}"))
+    for k, (t, val) in enumerate(so):
+        props.append(oh.SOOracle(params, val, t, halo_filter=so_filters[k] if so_filters else "basic"))
+    order = sorted(range(len(apertures)), key=lambda i: (apertures[i][0], apertures[i][2]))
+    prev = {}  # kind -> (radius, group name) of the previous aperture of that kind
+    for i, j in enumerate(order):
+        r, mpc, incl = apertures[j]
+        kind = "inclusive" if incl else "exclusive"
+        pr, pg = prev.get(kind, (None, None)) if kind in skip_gt else (None, None)
+        props.append(oh.ApertureOracle(params, r, mpc, bool(incl), f"{i}",
+                                       halo_filter=ap_filters[j] if ap_filters else "basic", prev_radius=pr,
+                                       prev_group=pg))
+        prev[kind] = (r, props[-1].group_name)
+    porder = sorted(range(len(projected)), key=lambda i: projected[i][0])
+    for i, j in enumerate(porder):
+        r, mpc = projected[j]
+        pr, pg = prev.get("projected", (None, None)) if "projected" in skip_gt else (None, None)
+        props.append(oh.ProjectedApertureOracle(params, r, mpc, f"{i}",
+                                                halo_filter=proj_filters[j] if proj_filters else "basic",
+                                                prev_radius=pr, prev_group=pg))
+        prev["projected"] = (r, props[-1].group_name)
     return props
 
 
-def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True, projected=(), iterative=False):
+def run_oracle(data, H, cp, so, apertures, faithful=False, halos=None, do_subhalo=True, projected=(), iterative=False,
+               filters=None, so_filters=None, ap_filters=None, proj_filters=None, mesh_resolution=None, skip_gt=()):
     """Returns list (per halo) of (halo_result or None, info, input_halo)."""
     params = oracle_params(cp, faithful)
     params.iterative_tensors = bool(iterative)
-    meshes = {t: om.MeshOracle(d["Coordinates"], om.mesh_resolution(len(d["Masses"]))) for t, d in data.items()}
-    props = oracle_prop_list(params, cp, so, apertures, do_subhalo, projected)
+    params.filters = dict(filters or {})
+    meshes = {t: om.MeshOracle(d["Coordinates"], mesh_resolution or om.mesh_resolution(len(d["Masses"])))
+              for t, d in data.items()}
+    props = oracle_prop_list(params, cp, so, apertures, do_subhalo, projected, so_filters, ap_filters, proj_filters, skip_gt)
     td = oh.target_density_of(props, params)
     out = []
     idxs = range(len(H["index"])) if halos is None else halos
