@@ -806,6 +806,12 @@ DevCfg make_devcfg(const soap_halo_config& c) {
         d.ap_r[a] = c.ap_radius[a]; d.ap_mpc[a] = c.ap_physical_mpc[a]; d.ap_incl[a] = c.ap_inclusive[a];
     }
     d.flags = c.property_flags;
+    d.n_filters = c.n_filters;
+    for (int f = 0; f < SOAP_MAX_FILTERS; f++) { d.filter_limit[f] = c.filter_limit[f]; d.filter_types[f] = c.filter_types[f]; }
+    for (int k = 0; k < SOAP_MAX_SO; k++) d.so_filter[k] = c.so_filter[k];
+    for (int a = 0; a < SOAP_MAX_APERTURES; a++) {
+        d.ap_filter[a] = c.ap_filter[a]; d.pj_filter[a] = c.proj_filter[a]; d.ap_prev[a] = c.ap_prev_radius[a];
+    }
     d.lay = row_layout(c);
     return d;
 }
@@ -823,6 +829,17 @@ int validate_cfg(const soap_halo_config* cfg) {
     if (cfg->n_projected > 0 && !cfg->do_subhalo)
         SOAP_FAIL("config: projected apertures need BoundSubhalo first (they assume every bound particle is loaded)");
     if (!(cfg->boxsize > 0.0)) SOAP_FAIL("config: boxsize must be positive");
+    if (cfg->n_filters < 0 || cfg->n_filters > SOAP_MAX_FILTERS)
+        SOAP_FAIL("config: n_filters=%d outside [0,%d]", cfg->n_filters, SOAP_MAX_FILTERS);
+    {
+        bool uses = false;
+        auto chk = [&](int f) { if (f < 0 || (f > 0 && f >= cfg->n_filters)) return false; if (f > 0) uses = true; return true; };
+        for (int k = 0; k < cfg->n_so; k++) if (!chk(cfg->so_filter[k])) SOAP_FAIL("config: so_filter[%d]=%d is not a filter index", k, cfg->so_filter[k]);
+        for (int a = 0; a < cfg->n_apertures; a++) if (!chk(cfg->ap_filter[a])) SOAP_FAIL("config: ap_filter[%d]=%d is not a filter index", a, cfg->ap_filter[a]);
+        for (int a = 0; a < cfg->n_projected; a++) if (!chk(cfg->proj_filter[a])) SOAP_FAIL("config: proj_filter[%d]=%d is not a filter index", a, cfg->proj_filter[a]);
+        // the filters read BoundSubhalo's particle counts (category_filter.py:91-102)
+        if (uses && !cfg->do_subhalo) SOAP_FAIL("config: category filters need BoundSubhalo (do_subhalo)");
+    }
     for (int a = 1; a < cfg->n_apertures; a++)
         if (cfg->ap_radius[a] < cfg->ap_radius[a - 1]) SOAP_FAIL("config: aperture radii must ascend");
     return 0;

@@ -30,6 +30,9 @@ struct ScanRes {
     uint32_t bound_count[4];
     int32_t cen_fof;
     int32_t so_exists[SOAP_MAX_SO];
+    // apertures / projected apertures committed at this rung that are actually computed (not filtered out,
+    // not skipped by the EncloseRadius shortcut); the others keep their zeros
+    uint32_t ap_on, pj_on;
 };
 
 // Selection block layout inside a result row (offsets relative to block start).
@@ -108,6 +111,12 @@ struct DevCfg {
     double ap_r[SOAP_MAX_APERTURES], ap_mpc[SOAP_MAX_APERTURES];
     int ap_incl[SOAP_MAX_APERTURES];
     uint32_t flags;
+    // CategoryFilter and the EncloseRadius shortcut (include/soap_b200.h)
+    int n_filters;
+    long long filter_limit[SOAP_MAX_FILTERS];
+    uint32_t filter_types[SOAP_MAX_FILTERS];
+    int so_filter[SOAP_MAX_SO], ap_filter[SOAP_MAX_APERTURES], pj_filter[SOAP_MAX_APERTURES];
+    double ap_prev[SOAP_MAX_APERTURES];
     RowLayout lay;
 };
 
@@ -176,6 +185,28 @@ struct Counters {
 };
 
 #ifdef __CUDACC__
+// CategoryFilter.get_do_calculation (category_filter.py:69-110) for filter f: bc = BoundSubhalo particle
+// counts by type code (gas, dm, star, bh)
+__device__ __forceinline__ bool filter_ok(const DevCfg& cfg, int f, const uint32_t* bc) {
+    if (f <= 0 || f >= cfg.n_filters) return true;  // "basic"
+    long long v = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        if ((cfg.filter_types[f] >> t) & 1u) v += bc[t];
+    return v >= cfg.filter_limit[f];
+}
+// What the commit logic does with aperture a: 0 = leave the zeros (filtered out, or an inclusive sphere the
+// previous radius of which already held every bound particle: aperture_properties.py:4082-4127),
+// 1 = compute it with the radius check of :4140-4143, 2 = compute it without (an exclusive sphere whose
+// previous radius held every bound particle equals that previous sphere; all its particles are loaded).
+__device__ __forceinline__ int aperture_mode(const DevCfg& cfg, int a, const uint32_t* bc, double enclose) {
+    const bool ok = filter_ok(cfg, cfg.ap_filter[a], bc);
+    // the reference compares with the float32 BoundSubhalo/EncloseRadius it stored
+    const bool skip = cfg.do_sub && cfg.ap_prev[a] >= 0.0 && cfg.ap_prev[a] > (double)(float)enclose;
+    if (!ok) return 0;
+    if (skip) return cfg.ap_incl[a] ? 0 : 2;
+    return 1;
+}
 // ------------------------------------------------------------------ ladder
 // halo_tasks.py:166-187 and :390-402.  Returns true if the halo stays pending.
 __device__ inline bool ladder_step(const HaloArrays& ha, uint32_t h, double required) {

@@ -158,7 +158,7 @@ __device__ inline void build_cuts(Cuts& c, const DevCfg& cfg, const ScanRes* sr,
     const bool sub_c = cfg.do_sub && c_lo == 0;
     c.n = 0;
     auto so_c = [&](int q) { return q < n_so && off_so + q >= c_lo && off_so + q < c_hi && sr->so_exists[q]; };
-    auto ap_c = [&](int a) { return a < cfg.n_ap && off_ap + a >= c_lo && off_ap + a < c_hi; };
+    auto ap_c = [&](int a) { return a < cfg.n_ap && off_ap + a >= c_lo && off_ap + a < c_hi && ((sr->ap_on >> a) & 1u); };
     for (int q = 0; q < n_so; q++)
         if (so_c(q)) add_cut(c, sr->so_r[q], 1, nullptr);
     if (sub_c && sr->sub_vmax_s_r > 0.0) add_cut(c, sr->sub_vmax_s_r, 0, nullptr);
@@ -465,7 +465,7 @@ __device__ inline int kappa_build_sels(KapSel* sel, const DevCfg& cfg, const Hal
         n++;
     }
     for (int a = 0; a < cfg.n_ap; a++)
-        if (off_ap + a >= c_lo && off_ap + a < c_hi) {
+        if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) {
             kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap);
             sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a];
             n++;
@@ -559,7 +559,7 @@ __device__ inline void kappa_finish_row(const DevCfg& cfg, const HaloArrays& ha,
     };
     if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
     for (int a = 0; a < cfg.n_ap; a++)
-        if (off_ap + a >= c_lo && off_ap + a < c_hi) fin(row + cfg.lay.ap[a], cfg.lay.bap);
+        if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) fin(row + cfg.lay.ap[a], cfg.lay.bap);
 }
 
 #endif  // __CUDACC__

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(TB) k_projected(ChunkView v, HaloArrays ha, De
             __syncthreads();
         }
         // ------------------------------------------------- rows: one thread per (radius, axis)
-        if ((int)threadIdx.x < npj * 3) {
+        if ((int)threadIdx.x < npj * 3 && ((ha.sres[h].pj_on >> (threadIdx.x / 3)) & 1u)) {
             const int p = threadIdx.x / 3, ax = threadIdx.x % 3;
             double* blk = ha.out + (int64_t)h * ha.ncol + cfg.lay.pj[p] + ax * cfg.lay.pjb;
             double S[4][PV], T[PV];

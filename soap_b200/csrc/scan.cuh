@@ -686,6 +686,17 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
             int p = p0;
             const double r_last = n > 0 ? __longlong_as_double((long long)R[n - 1].rbits) : 0.0;
             for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; S.so_r_[q] = 0.0; }
+            // BoundSubhalo's particle counts and enclosing radius: of this rung if it is committed now, else as stored
+            uint32_t bc[4];
+            double enclose = 0.0;
+            if (p0 == 0) {
+                for (int ty = 0; ty < 4; ty++) bc[ty] = NCH == 2 ? (ty == 1 ? S.cnt[1] : 0u) : S.cnt[(2 * ty + 1) % NCH];
+                for (int ch = 1; ch < NCH; ch += 2) enclose = fmax(enclose, S.rmaxc[ch]);
+            } else {
+                for (int ty = 0; ty < 4; ty++) bc[ty] = sr->bound_count[ty];
+                enclose = sr->sub_enclose;
+            }
+            uint32_t ap_on = 0, pj_on = 0;
             while (p < nprops && !fail) {
                 if (p < off_so) {
                     // BoundSubhalo particle count (subhalo_properties.py:2632-2646)
@@ -694,7 +705,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                     else if (Ntot > Nexp) { fail = 2; status = SOAP_HALO_COUNT_MISMATCH; }
                 } else if (p < off_ap) {
                     const int q = p - off_so;
-                    if (central) {
+                    if (central && filter_ok(cfg, cfg.so_filter[q], bc)) {  // SO_properties.py:3627
                 const int sf = S.par_fail[q];
                 double SO_r = S.par_r[q], SO_mass = S.par_mass[q];
                 if (sf) { fail = sf; status = S.par_status[q]; required = 0.0; }
@@ -706,15 +717,20 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 }
                     }
                 } else if (p < off_pj) {
-                    // apertures ascending (aperture_properties.py:4140-4143)
+                    // apertures ascending (aperture_properties.py:4082-4143)
                     const int a = p - off_ap;
-                    if (ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+                    const int mode = aperture_mode(cfg, a, bc, enclose);
+                    if (mode == 1 && ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+                    if (mode != 0 && !fail) ap_on |= 1u << a;
                 } else {
                     // projected apertures use bound particles only and never ask for a
                     // larger radius (projected_aperture_properties.py:1888-1892)
+                    if (filter_ok(cfg, cfg.pj_filter[p - off_pj], bc)) pj_on |= 1u << (p - off_pj);
                 }
                 if (!fail) p++;
             }
+            sr->ap_on = ap_on;
+            sr->pj_on = pj_on;
             ha.commit_lo[h] = p0;
             ha.commit_hi[h] = p;
             ha.ndone[h] = p;

@@ -338,6 +338,19 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
     int p = p0;
     double so_r_[SOAP_MAX_SO];
     for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; so_r_[q] = 0.0; }
+    // BoundSubhalo's particle counts and enclosing radius: of this rung if it is committed now, else as stored
+    uint32_t bc[4];
+    double enclose = 0.0;
+    if (p0 == 0) {
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++) bc[ty] = NCH == 2 ? (ty == 1 ? cnt[1] : 0u) : cnt[(2 * ty + 1) % NCH];
+#pragma unroll
+        for (int ch = 1; ch < NCH; ch += 2) enclose = fmax(enclose, rmaxc[ch]);
+    } else {
+        for (int ty = 0; ty < 4; ty++) bc[ty] = sr->bound_count[ty];
+        enclose = sr->sub_enclose;
+    }
+    uint32_t ap_on = 0, pj_on = 0;
     while (p < nprops && !fail) {
         if (p < off_so) {
             // BoundSubhalo particle count (subhalo_properties.py:2632-2646)
@@ -346,7 +359,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
             else if (Ntot > Nexp) { fail = 2; status = SOAP_HALO_COUNT_MISMATCH; }
         } else if (p < off_ap) {
             const int q = p - off_so;
-            if (central) {
+            if (central && filter_ok(cfg, cfg.so_filter[q], bc)) {  // SO_properties.py:3627
                 const int sf = par_fail[q];
                 if (sf) { fail = sf; status = par_status[q]; required = 0.0; }
                 if (!fail) {
@@ -358,15 +371,21 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
                 }
             }
         } else if (p < off_pj) {
-            // apertures ascending (aperture_properties.py:4140-4143)
+            // apertures ascending (aperture_properties.py:4082-4143)
             const int a = p - off_ap;
-            if (ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+            const int mode = aperture_mode(cfg, a, bc, enclose);
+            if (mode == 1 && ha.cur_r[h] < cfg.ap_r[a]) { fail = 1; required = cfg.ap_mpc[a] * cfg.mpc2c; }
+            if (mode != 0 && !fail) ap_on |= 1u << a;
+        } else {
+            // projected apertures use bound particles only and never ask for a larger radius
+            // (projected_aperture_properties.py:1888-1892)
+            if (filter_ok(cfg, cfg.pj_filter[p - off_pj], bc)) pj_on |= 1u << (p - off_pj);
         }
-        // projected apertures use bound particles only and never ask for a larger radius
-        // (projected_aperture_properties.py:1888-1892)
         if (!fail) p++;
     }
     const int c_lo = p0, c_hi = p;
+    sr->ap_on = ap_on;
+    sr->pj_on = pj_on;
     ha.commit_lo[h] = c_lo;
     ha.commit_hi[h] = c_hi;
     ha.ndone[h] = p;

@@ -53,6 +53,18 @@ class HaloPropConfig:
     dmo: bool = False
     # cross-check switch (bit 0: every halo through the general kernel-sequence path); 0 in production
     debug_flags: int = 0
+    # CategoryFilter (category_filter.py:69-110): name -> (limit, ptypes whose BoundSubhalo counts are summed);
+    # "basic" is implicit.  so_filter / ap_filter / proj_filter give the halo_filter name of each variation,
+    # aligned with ``so`` / ``apertures`` / ``projected`` as given (default "basic").
+    filters: Dict[str, tuple] = field(default_factory=dict)
+    so_filter: List[str] = field(default_factory=list)
+    ap_filter: List[str] = field(default_factory=list)
+    proj_filter: List[str] = field(default_factory=list)
+    # aperture kinds ("exclusive", "inclusive") whose variations know the radii of their siblings
+    # (all_radii_kpc; compute_halo_properties.py:345-395 always passes them to exclusive spheres, to inclusive
+    # ones with skip_gt_enclose_radius) and therefore use the EncloseRadius shortcut (needs
+    # BoundSubhalo/EncloseRadius to be enabled in the parameter file)
+    skip_gt: tuple = ()
 
     def so_reference_density(self, i):
         """SO_properties.py:3494-3512."""
@@ -100,14 +112,44 @@ class HaloPropConfig:
         for i in range(len(self.so)):
             c.so_reference_density[i] = float(self.so_reference_density(i))
             c.so_virial[i] = int(self.so_virial(i))
-        aps = sorted(self.apertures, key=lambda a: (a[0], a[2]))
+        # filters: index 0 is "basic"
+        fnames = ["basic"] + [n for n in self.filters if n != "basic"]
+        if len(fnames) > _lib.SOAP_MAX_FILTERS:
+            raise ValueError("too many category filters")
+        c.n_filters = len(fnames)
+        code = {0: 0, 1: 1, 4: 2, 5: 3}
+        for f, name in enumerate(fnames[1:], start=1):
+            limit, ptypes = self.filters[name]
+            c.filter_limit[f] = int(limit)
+            c.filter_types[f] = sum(1 << code[int(str(t)[-1])] for t in ptypes)
+
+        def fidx(lst, i):
+            name = lst[i] if i < len(lst) else "basic"
+            if name not in fnames:
+                raise KeyError(f'filter "{name}" is not defined')
+            return fnames.index(name)
+
+        for i in range(len(self.so)):
+            c.so_filter[i] = fidx(self.so_filter, i)
+        order = sorted(range(len(self.apertures)), key=lambda i: (self.apertures[i][0], self.apertures[i][2]))
+        aps = [self.apertures[i] for i in order]
         self._sorted_apertures = aps
         c.n_apertures = len(aps)
+        for i in range(_lib.SOAP_MAX_APERTURES):
+            c.ap_prev_radius[i] = -1.0
+            c.proj_prev_radius[i] = -1.0
+        prev = {}
         for i, (r, mpc, incl) in enumerate(aps):
             c.ap_radius[i] = float(r)
             c.ap_physical_mpc[i] = float(mpc)
             c.ap_inclusive[i] = int(bool(incl))
-        pj = sorted(self.projected, key=lambda a: a[0])
+            c.ap_filter[i] = fidx(self.ap_filter, order[i])
+            kind = "inclusive" if incl else "exclusive"
+            if kind in self.skip_gt and kind in prev:
+                c.ap_prev_radius[i] = float(prev[kind])
+            prev[kind] = r
+        porder = sorted(range(len(self.projected)), key=lambda i: self.projected[i][0])
+        pj = [self.projected[i] for i in porder]
         if len(pj) > _lib.SOAP_MAX_APERTURES:
             raise ValueError("too many projected aperture variations")
         self._sorted_projected = pj
@@ -115,12 +157,9 @@ class HaloPropConfig:
         for i, (r, mpc) in enumerate(pj):
             c.proj_radius[i] = float(r)
             c.proj_physical_mpc[i] = float(mpc)
+            c.proj_filter[i] = fidx(self.proj_filter, porder[i])
         c.property_flags = int(self.property_flags)
         c.dmo = int(self.dmo)
-        c.n_filters = 0
-        for i in range(_lib.SOAP_MAX_APERTURES):
-            c.ap_prev_radius[i] = -1.0
-            c.proj_prev_radius[i] = -1.0
         c.debug_flags = int(self.debug_flags)
         return c
 

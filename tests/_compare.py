@@ -23,10 +23,13 @@ def oracle_params(cp, faithful=False):
     )
 
 
-def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True, projected=()):
+def device_config(cp, so=(), apertures=(), flags=0, dmo=False, do_subhalo=True, projected=(), filters=None,
+                  so_filters=None, ap_filters=None, proj_filters=None, skip_gt=()):
     from soap_b200.halo_tasks import HaloPropConfig
 
     return HaloPropConfig(
+        filters=dict(filters or {}), so_filter=list(so_filters or []), ap_filter=list(ap_filters or []),
+        proj_filter=list(proj_filters or []), skip_gt=tuple(skip_gt),
         boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
         mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
         H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
@@ -142,9 +145,13 @@ class Report:
         assert not self.bad, "parity failures (first 10): " + "\n".join(str(b) for b in self.bad[:10])
 
 
-def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
-    """res: HaloResults of the device path; oracle_out from run_oracle."""
+def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None, faithful=False):
+    """res: HaloResults of the device path; oracle_out from run_oracle.  faithful = the oracle ran in its
+    dtype-for-dtype mode (float32 sums where the reference has them): SURVEY.md Appendix B allows 4e-6 there
+    for the 1e-6 class (numpy's pairwise float32 sums carry that much noise themselves)."""
     rep = rep or Report()
+    TOL_MASS_RADIUS = 4e-6 if faithful else 1e-6
+    TOL_FIRST_MOMENT = 4e-5 if faithful else 1e-5
     L = cp["boxsize"]
     names = _group_names(props)
     status = res.status.cpu().numpy()
@@ -203,13 +210,19 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None):
                 rep.check(pre + "vcom", h, g("vcom"), o["vcom"], TOL_FIRST_MOMENT, scale=300.0)
             else:
                 rep.check(pre + "com", h, g("com"), np.zeros(3), 0, exact=True)
+            # get_vmax sums the masses with a float32 cumsum (kinematic_properties.py:583): the reference's own
+            # Vmax carries up to n * 2^-24 of rounding, which the faithful oracle reproduces and the float64
+            # device sums do not (the float64 oracle comparison keeps the plain tolerance)
+            nsel = sum(float(o.get(k, 0)) for k in ("Ngas", "Ndm", "Nstar", "Nbh"))
+            tol_vmax = TOL_MASS_RADIUS + (nsel * 2.0**-24 if faithful else 0.0)
             if kind in ("so", "sub"):
-                rep.check(pre + "Vmax_soft", h, g("Vmax_soft"), o.get("Vmax_soft", 0.0), TOL_MASS_RADIUS)
+                rep.check(pre + "Vmax_soft", h, g("Vmax_soft"), o.get("Vmax_soft", 0.0), tol_vmax)
                 rep.check(pre + "R_vmax_soft", h, g("R_vmax_soft"), o.get("R_vmax_soft", 0.0), TOL_MASS_RADIUS)
-                rep.check(pre + "spin_parameter", h, g("spin_parameter"), o.get("spin_parameter", 0.0), TOL_SECOND)
+                rep.check(pre + "spin_parameter", h, g("spin_parameter"), o.get("spin_parameter", 0.0), TOL_SECOND + tol_vmax)
             if kind == "sub":
-                for k in ("EncloseRadius", "R_vmax_unsoft", "Vmax_unsoft", "HalfMassRadiusTot"):
+                for k in ("EncloseRadius", "R_vmax_unsoft", "HalfMassRadiusTot"):
                     rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_MASS_RADIUS)
+                rep.check(pre + "Vmax_unsoft", h, g("Vmax_unsoft"), o.get("Vmax_unsoft", 0.0), tol_vmax)
             if kind == "so":
                 rep.check(pre + "r", h, g("r"), o.get("r", 0.0), TOL_MASS_RADIUS)
                 rep.check(pre + "Mso", h, g("Mso"), o.get("Mtot", 0.0), TOL_MASS_RADIUS)
