@@ -26,6 +26,7 @@ struct ScanRes {
     double sub_hmr[5];  // tot, gas, dm, star, baryon
     double sub_enclose;
     double ap_hmr[SOAP_MAX_APERTURES][4];  // gas, dm, star, baryon
+    double ap_vmax_r[SOAP_MAX_APERTURES], ap_vmax_v[SOAP_MAX_APERTURES];  // Vmax_soft of the aperture (v = cum / r)
     double bound_mass[4];
     uint32_t bound_count[4];
     int32_t cen_fof;

@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(128) k_rows(HaloArrays ha, DevCfg cfg, const u
 __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, DevCfg cfg, const Item* __restrict__ items,
                                               const unsigned int* __restrict__ n_items_dev) {
     __shared__ SweepShared SW;
-    __shared__ KapSel sel[1 + SOAP_MAX_APERTURES];
-    __shared__ double acc[1 + SOAP_MAX_APERTURES][11];
+    __shared__ KapSel sel[KAPPA_MAX_SEL];
+    __shared__ double acc[KAPPA_MAX_SEL][11];
     __shared__ int nsel;
     const unsigned int n_items = *n_items_dev;
     for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, Dev
         const int64_t hidx = ha.index[h];
         __syncthreads();
         if (threadIdx.x == 0) nsel = kappa_build_sels(sel, cfg, ha, h, c_lo, c_hi);
-        for (int i = threadIdx.x; i < (1 + SOAP_MAX_APERTURES) * 11; i += TB) (&acc[0][0])[i] = 0.0;
+        for (int i = threadIdx.x; i < KAPPA_MAX_SEL * 11; i += TB) (&acc[0][0])[i] = 0.0;
         __syncthreads();
         const int ns = nsel;
         if (ns == 0) continue;

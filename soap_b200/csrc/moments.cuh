@@ -383,6 +383,9 @@ __device__ void write_row(const double* banks, const Cuts& cuts, int ncut, const
                 double* blk = row + L.ap[a];
                 write_block<V>(blk, L.bap, S, centre, cfg, cfg.flags);
                 if ((cfg.flags & PF_ITER) && L.bap.tens >= 0) blk[L.bap.tens + 12] = ha.rung_r[h];  // iter.cu
+                // aperture_properties.py:3553-3577
+                blk[15] = blk[8] != 0.0 ? sqrt(sr->ap_vmax_v[a] * cfg.G) : 0.0;
+                blk[16] = blk[8] != 0.0 ? sr->ap_vmax_r[a] : 0.0;
                 if (cfg.flags & PF_HMR)
                     for (int g = 0; g < 4; g++) blk[L.bap.hmr + g] = sr->ap_hmr[a][g];
                 if ((cfg.flags & PF_TENS) && S[2][V_M] != 0.0) {
@@ -410,9 +413,10 @@ struct KapSel {
     double ex[3], ey[3];  // in-plane axes of the stellar frame (cylindrical_coordinates.py:13-42)
     int cyl_ok;           // Nstar >= 2 and sum(Lstar) != 0 (aperture_properties.py:1483-1490)
     double R;
-    int incl, is_sub;
+    int incl, is_sub, strict;  // strict: r < R (SO selections, SO_properties.py:485) instead of r <= R
     double* out;  // the block's 11 kappa / rotation slots
 };
+constexpr int KAPPA_MAX_SEL = 1 + SOAP_MAX_SO + SOAP_MAX_APERTURES;
 
 __device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl) {
     const double* kin = blk + bl.kin;
@@ -461,13 +465,24 @@ __device__ inline int kappa_build_sels(KapSel* sel, const DevCfg& cfg, const Hal
     int n = 0;
     if (cfg.do_sub && c_lo == 0) {
         kappa_refs(sel[n], row + cfg.lay.sub, cfg.lay.bsub);
-        sel[n].is_sub = 1; sel[n].incl = 0; sel[n].R = 0.0;
+        sel[n].is_sub = 1; sel[n].incl = 0; sel[n].R = 0.0; sel[n].strict = 0;
         n++;
+    }
+    // SO variations: every particle inside the SO radius (DtoTgas / DtoTstar of SOProperties)
+    {
+        const int off_so = cfg.do_sub ? 1 : 0;
+        const ScanRes* sr = ha.sres + h;
+        for (int q = 0; q < cfg.n_so; q++)
+            if (off_so + q >= c_lo && off_so + q < c_hi && sr->so_exists[q]) {
+                kappa_refs(sel[n], row + cfg.lay.so[q], cfg.lay.bso);
+                sel[n].is_sub = 0; sel[n].incl = 1; sel[n].R = sr->so_r[q]; sel[n].strict = 1;
+                n++;
+            }
     }
     for (int a = 0; a < cfg.n_ap; a++)
         if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) {
             kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap);
-            sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a];
+            sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a]; sel[n].strict = 0;
             n++;
         }
     return n;
@@ -481,7 +496,7 @@ __device__ __forceinline__ void kappa_add(const KapSel* sel, int ns, double (*ac
     const int g0 = tc == 0u ? 0 : 1;
     for (int s = 0; s < ns; s++) {
         const KapSel& k = sel[s];
-        const bool in = k.is_sub ? bound : (r <= k.R && (k.incl || bound));
+        const bool in = k.is_sub ? bound : ((k.strict ? r < k.R : r <= k.R) && (k.incl || bound));
         if (!in) continue;
         for (int gi = 0; gi < 2; gi++) {
             const int g = gi == 0 ? g0 : 2;
@@ -558,6 +573,9 @@ __device__ inline void kappa_finish_row(const DevCfg& cfg, const HaloArrays& ha,
         }
     };
     if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
+    for (int q = 0; q < cfg.n_so; q++)
+        if ((cfg.do_sub ? 1 : 0) + q >= c_lo && (cfg.do_sub ? 1 : 0) + q < c_hi && ha.sres[h].so_exists[q])
+            fin(row + cfg.lay.so[q], cfg.lay.bso);
     for (int a = 0; a < cfg.n_ap; a++)
         if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) fin(row + cfg.lay.ap[a], cfg.lay.bap);
 }

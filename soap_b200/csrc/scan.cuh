@@ -83,6 +83,10 @@ struct ScanShared {
     // argmax block reduce
     double am_v[NT / 32], am_r[NT / 32];
     uint32_t am_i[NT / 32];
+    // aperture Vmax_soft: first maximum of cum / max(soft, r) per radial shell between aperture edges,
+    // kind 0 = all records, 1 = bound records (published per CTA, merged by rank 0)
+    double apv_v[2][SOAP_MAX_APERTURES], apv_r[2][SOAP_MAX_APERTURES];
+    uint32_t apv_i[2][SOAP_MAX_APERTURES];
 };
 
 // class of a record: type index * 2 + bound (DMO: type index 0)
@@ -828,7 +832,7 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         const int c_so_lo = cfg.do_sub ? 1 : 0, c_ap_lo = c_so_lo + cfg.n_so;
         const bool so_committed = n_so > 0 && S.commit_hi_ > S.commit_lo_ && S.commit_lo_ < c_ap_lo && S.commit_hi_ > c_so_lo;
         const bool ap_committed = n_ap > 0 && S.commit_hi_ > c_ap_lo && S.commit_hi_ > S.commit_lo_;
-        const bool need_c = S.fail_ < 2 && (so_committed || (ap_committed && want_hmr));
+        const bool need_c = S.fail_ < 2 && (so_committed || ap_committed);
         if (ALIGN) align_bar(2);
         // (uniform over the cluster: everyone leaves or everyone stays)
         if (!need_c) { csync(); return; }
@@ -839,6 +843,15 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
         ArgMax amSO[SOAP_MAX_SO];
 #pragma unroll
         for (int q = 0; q < SOAP_MAX_SO; q++) amSO[q].init();
+        // aperture Vmax_soft (aperture_properties.py:3553-3577): a record lies in exactly one shell between
+        // aperture edges, so one tracker per (kind, shell) is touched per record (local memory); an aperture's
+        // maximum is the first maximum over its shells
+        ArgMax amAP[2][SOAP_MAX_APERTURES];
+        for (int a = 0; a < n_ap; a++) { amAP[0][a].init(); amAP[1][a].init(); }
+        uint32_t NA0 = 0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) NA0 += S.cnt0[ch];
+        const uint32_t nskip_all = (min_soft <= 1e-8) ? (NA0 < n ? NA0 : 0u) : 0u;
         for (uint32_t tile = t_lo; tile < t_hi; tile++) {
             const uint32_t i0 = tile * TILE + gt * K;
             Rec rc[K];
@@ -872,11 +885,27 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                 const uint32_t tc = NCH == 2 ? 1u : (rc[k].flags & 3u);
                 const bool bound = (rc[k].flags & 4u) != 0;
                 const uint32_t pos_all = all_cnt<NCH>(basec);
+                const uint32_t posb = bound_cnt<NCH>(basec);
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++)
                     if (c == ch) { base[ch] += m; basec[ch]++; }
                 const double call_in = all_sum<NCH>(base);
                 const double rs = fmax(cfg.soft[tc], r);
+                if (ap_committed && rs > 0.0) {
+                    int sh = 0;
+                    while (sh < n_ap && r > cfg.ap_r[sh]) sh++;
+                    if (sh < n_ap) {
+                        if (pos_all >= nskip_all) {
+                            ArgMax& t = amAP[0][sh];
+                            if (call_in >= t.v * rs - 1e-12 * fabs(t.v * rs)) t.offer(call_in / rs, rs, i);
+                        }
+                        if (bound && posb >= nskip_s) {
+                            const double cb_in = bound_sum<NCH>(base);
+                            ArgMax& t = amAP[1][sh];
+                            if (cb_in >= t.v * rs - 1e-12 * fabs(t.v * rs)) t.offer(cb_in / rs, rs, i);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < SOAP_MAX_SO; q++)
                     if (q < n_so && S.so_r_[q] > 0.0) {
@@ -956,12 +985,32 @@ __device__ void scan_solve_halo(ScanShared<NCH, NT>& S, const HaloArrays& ha, co
                     S.pub_v[2 + q] = amSO[q].v; S.pub_r[2 + q] = amSO[q].r; S.pub_i[2 + q] = amSO[q].i;
                 }
             }
+        if (ap_committed)
+            for (int kd = 0; kd < 2; kd++)
+                for (int a = 0; a < n_ap; a++) {
+                    ArgMax t = amAP[kd][a];
+                    argmax_reduce<NCH, NT>(t, S);
+                    if (gt == 0) { S.apv_v[kd][a] = t.v; S.apv_r[kd][a] = t.r; S.apv_i[kd][a] = t.i; }
+                }
         if (CS > 1) {
             csync();  // every CTA's pass C results are visible
             merge_targets();
         }
         gsync<NT>();
         if (gt == 0 && crank == 0) {
+            if (ap_committed)
+                for (int a = 0; a < n_ap; a++) {
+                    const int kd = cfg.ap_incl[a] ? 0 : 1;
+                    ArgMax best;
+                    best.init();
+                    for (int sh = 0; sh <= a; sh++)
+                        for (unsigned int rk = 0; rk < CS; rk++) {
+                            const ScanShared<NCH, NT>* P = peer(rk);
+                            best.offer(P->apv_v[kd][sh], P->apv_r[kd][sh], P->apv_i[kd][sh]);
+                        }
+                    sr->ap_vmax_r[a] = best.i == NONE ? 0.0 : best.r;
+                    sr->ap_vmax_v[a] = best.i == NONE ? 0.0 : best.v;
+                }
 #pragma unroll
             for (int q = 0; q < SOAP_MAX_SO; q++)
                 if (q < n_so) {

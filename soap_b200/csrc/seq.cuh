@@ -424,7 +424,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
     // pass C serves the SOs and apertures committed at this rung
     const bool so_committed = n_so > 0 && c_hi > c_lo && c_lo < off_ap && c_hi > off_so;
     const bool ap_committed = n_ap > 0 && c_hi > off_ap && c_hi > c_lo;
-    const bool need_c = fail < 2 && (so_committed || (ap_committed && want_hmr));
+    const bool need_c = fail < 2 && (so_committed || ap_committed);
     if (need_c) {
         // ------------------------------------------------------------ pass C
         // the SO radii ascending: the records offered to a variation are a prefix of the sorted profile,
@@ -461,6 +461,22 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         for (int b = 0; b < 2; b++)
             for (int g = 0; g < 4; g++) last_m[b][g] = 0.0;
         int a_lo = 0;  // apertures below a_lo lie inside the current radius
+        // Vmax_soft of the apertures (aperture_properties.py:3553-3577): running first maximum of cum / max(soft, r)
+        // over all records (inclusive spheres) and over the bound ones (exclusive), closed at each aperture edge
+        uint32_t NA0 = 0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) NA0 += cnt0[ch];
+        const uint32_t nskip_all = (min_soft <= 1e-8) ? (NA0 < n ? NA0 : 0u) : 0u;
+        double bA_c = 0.0, bA_r = 0.0, bB_c = 0.0, bB_r = 0.0, cum_bnd = 0.0;
+        bool bA_ok = false, bB_ok = false;
+        uint32_t nb_seen = 0;
+        int a_v = 0;
+        auto close_ap = [&](int a) {
+            const bool incl = cfg.ap_incl[a] != 0;
+            const bool ok = incl ? bA_ok : bB_ok;
+            sr->ap_vmax_r[a] = ok ? (incl ? bA_r : bB_r) : 0.0;
+            sr->ap_vmax_v[a] = ok ? (incl ? bA_c / bA_r : bB_c / bB_r) : 0.0;
+        };
         rs.finish();
         rs.start();
         for (uint32_t i = 0; i < n; i++) {
@@ -483,6 +499,19 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
                 if (c == ch) base[ch] += m;
             cum_all += m;
             const double rs = fmax(cfg.soft[tc], r);
+            if (n_ap > 0) {
+                while (a_v < n_ap && r > cfg.ap_r[a_v]) close_ap(a_v++);
+                const uint32_t nb_before = nb_seen;
+                if (bound) { cum_bnd += m; nb_seen++; }
+                if (a_v < n_ap && rs > 0.0) {
+                    if (i >= nskip_all && (!bA_ok || quotient_greater(cum_all, rs, bA_c, bA_r))) {
+                        bA_c = cum_all; bA_r = rs; bA_ok = true;
+                    }
+                    if (bound && nb_before >= nskip_s && (!bB_ok || quotient_greater(cum_bnd, rs, bB_c, bB_r))) {
+                        bB_c = cum_bnd; bB_r = rs; bB_ok = true;
+                    }
+                }
+            }
             // Vmax_soft inside each SO (SO_properties.py:573-600): close the variations this record lies outside of
             while (next_v < nq && !(r < bound_v)) {
                 const int q = qs[next_v];
@@ -527,6 +556,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
                     }
             }
         }
+        while (a_v < n_ap) close_ap(a_v++);
         for (; next_v < nq; next_v++) {
             const int q = qs[next_v];
             sr->so_vmax_r[q] = best_ok ? best_r : 0.0;

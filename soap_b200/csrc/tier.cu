@@ -480,12 +480,11 @@ __global__ void __launch_bounds__(32 * NW) k_tier_kappa(ChunkView v, HaloArrays 
                                                         const unsigned int* __restrict__ n_list,
                                                         const Rec* __restrict__ recs,
                                                         const uint32_t* __restrict__ pids) {
-    constexpr int KS = 1 + SOAP_MAX_APERTURES;
-    __shared__ KapSel ksel_s[NW][KS];
-    __shared__ double kacc_s[NW][KS][11];
+    constexpr int KS = KAPPA_MAX_SEL;
+    extern __shared__ __align__(16) unsigned char kappa_smem[];  // [NW] x (KapSel[KS], double[KS][11])
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    KapSel* ksel = ksel_s[wid];
-    double(*kacc)[11] = kacc_s[wid];
+    KapSel* ksel = reinterpret_cast<KapSel*>(kappa_smem + (size_t)wid * KS * (sizeof(KapSel) + 11 * sizeof(double)));
+    double(*kacc)[11] = reinterpret_cast<double(*)[11]>(ksel + KS);
     const double L = v.L, halfL = 0.5 * v.L;
     const unsigned int n_total = *n_list;
     for (unsigned int it = blockIdx.x * NW + wid; it < n_total; it += gridDim.x * NW) {
@@ -611,7 +610,9 @@ int soap_tier_round(soap_chunk* c, const DevCfg& cfg, HaloArrays& ha, int tier, 
         unsigned int grid = (unsigned int)(h->sm_count * 4);
         const unsigned int need = (n_upper + NW - 1) / NW;
         if (grid > need) grid = need < 1 ? 1 : need;
-        LAUNCH(h, k_tier_kappa<NW>, grid, 32 * NW, 0, stream, c->v, ha, cfg, try_list, &ctr->n_try, recs, pids);
+        const size_t ksm = (size_t)NW * KAPPA_MAX_SEL * (sizeof(KapSel) + 11 * sizeof(double));
+        CUDA_TRY(cudaFuncSetAttribute(k_tier_kappa<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));
+        LAUNCH(h, k_tier_kappa<NW>, grid, 32 * NW, ksm, stream, c->v, ha, cfg, try_list, &ctr->n_try, recs, pids);
         if (soap_launch_kappa_finish(h, cfg, ha, try_list, &ctr->n_try, n_upper, stream)) return -1;
     }
     return 0;

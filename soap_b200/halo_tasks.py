@@ -65,6 +65,12 @@ class HaloPropConfig:
     # ones with skip_gt_enclose_radius) and therefore use the EncloseRadius shortcut (needs
     # BoundSubhalo/EncloseRadius to be enabled in the parameter file)
     skip_gt: tuple = ()
+    # exact values read from the reference's property objects (dropin.py), used instead of the ones derived
+    # from ``so`` when given: SOProperties.reference_density / .virial_definition and the target density of
+    # halo_tasks.py:306-317
+    so_rho: Optional[List[float]] = None
+    so_virial_flags: Optional[List[bool]] = None
+    target_density_value: Optional[float] = None
 
     def so_reference_density(self, i):
         """SO_properties.py:3494-3512."""
@@ -103,15 +109,15 @@ class HaloPropConfig:
         c.phys_mpc_to_coord = self.phys_mpc_to_coord
         for pt in range(_lib.SOAP_MAX_PTYPES):
             c.softening[pt] = float(self.softening.get(pt, 0.0))
-        td = self.target_density()
+        td = self.target_density() if self.target_density_value is None else self.target_density_value
         c.target_density = -1.0 if td is None else float(td)
         c.do_subhalo = int(self.do_subhalo)
         if len(self.so) > _lib.SOAP_MAX_SO or len(self.apertures) > _lib.SOAP_MAX_APERTURES:
             raise ValueError("too many SO / aperture variations")
         c.n_so = len(self.so)
         for i in range(len(self.so)):
-            c.so_reference_density[i] = float(self.so_reference_density(i))
-            c.so_virial[i] = int(self.so_virial(i))
+            c.so_reference_density[i] = float(self.so_reference_density(i) if self.so_rho is None else self.so_rho[i])
+            c.so_virial[i] = int(self.so_virial(i) if self.so_virial_flags is None else self.so_virial_flags[i])
         # filters: index 0 is "basic"
         fnames = ["basic"] + [n for n in self.filters if n != "basic"]
         if len(fnames) > _lib.SOAP_MAX_FILTERS:

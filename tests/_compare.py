@@ -219,6 +219,9 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None, faithful=
                 rep.check(pre + "Vmax_soft", h, g("Vmax_soft"), o.get("Vmax_soft", 0.0), tol_vmax)
                 rep.check(pre + "R_vmax_soft", h, g("R_vmax_soft"), o.get("R_vmax_soft", 0.0), TOL_MASS_RADIUS)
                 rep.check(pre + "spin_parameter", h, g("spin_parameter"), o.get("spin_parameter", 0.0), TOL_SECOND + tol_vmax)
+            if kind == "ap":  # aperture_properties.py:3553-3577
+                rep.check(pre + "Vmax_soft", h, g("Vmax_soft"), o.get("Vmax_soft", 0.0), tol_vmax)
+                rep.check(pre + "R_vmax_soft", h, g("R_vmax_soft"), o.get("R_vmax_soft", 0.0), TOL_MASS_RADIUS)
             if kind == "sub":
                 for k in ("EncloseRadius", "R_vmax_unsoft", "HalfMassRadiusTot"):
                     rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_MASS_RADIUS)
@@ -255,6 +258,10 @@ def compare(res, oracle_out, props, cp, halos=None, flags=0, rep=None, faithful=
                     ek = float(o["KineticEnergyTotal"])
                     rep.check(pre + "Ekin_tot", h, g("Ekin_tot"), ek, TOL_SECOND,
                               scale=max(abs(ek), 1e-3 * o["Mtot"] * 300.0**2))
+            if flags & 2 and kind == "so":
+                # SOProperties has the disc fractions only
+                for k in ("DtoTgas", "DtoTstar"):
+                    rep.check(pre + k, h, g(k), o.get(k, 0.0), TOL_SECOND, scale=1.0)
             if flags & 2 and kind in ("sub", "ap"):
                 # kappa_corot / DtoT are ratios of second moments: absolute tolerance
                 for k in ("kappa_corot_gas", "kappa_corot_star", "kappa_corot_baryons", "DtoTgas", "DtoTstar"):

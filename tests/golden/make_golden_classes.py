@@ -237,6 +237,28 @@ def main():
                         if g not in groups:
                             groups.append(g)
         out.setdefault("n_loop", np.zeros(n_h, dtype=np.int64))[i] = int(np.asarray(res["InputHalos/n_loop"][0])) if "InputHalos/n_loop" in res else 0
+    # what the drop-in adapter reads from the reference's property objects, for duck-typed stand-ins on hosts
+    # without /root/reference (tests/test_dropin.py)
+    import json
+
+    meta = []
+    for hp in props:
+        ent = {"class": hp.__class__.__name__, "base_halo_type": hp.base_halo_type, "group_name": hp.group_name,
+               "halo_filter": hp.halo_filter, "physical_radius_mpc": float(hp.physical_radius_mpc),
+               "mean_density_multiple": None if hp.mean_density_multiple is None else float(hp.mean_density_multiple),
+               "critical_density_multiple": None if hp.critical_density_multiple is None else float(hp.critical_density_multiple)}
+        for k in ("type", "virial_definition", "inclusive", "all_radii_kpc", "aperture_physical_radius_kpc", "label"):
+            if hasattr(hp, k):
+                v = getattr(hp, k)
+                ent[k] = v if isinstance(v, (str, bool, list, type(None))) else float(v)
+        if hasattr(hp, "reference_density"):
+            ent["reference_density"] = float(hp.reference_density)
+        ent["properties"] = [[name, prop.name, int(prop.shape), np.dtype(prop.dtype).name, str(prop.unit), str(prop.description),
+                              bool(prop.output_physical), prop.a_scale_exponent, bool(prop.dmo_property),
+                              hp.property_filters[prop.name]] for name, prop in hp.property_list.items()
+                             if hp.property_filters[prop.name]]
+        meta.append(ent)
+    out["meta_json"] = np.array(json.dumps(meta))
     out["groups"] = np.array(groups)
     out["done"] = done
     out["search_radius_out"] = sr_out
