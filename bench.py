@@ -47,22 +47,51 @@ WORKLOADS = {
     "config3": (2 * 256**3, 50000, 142.2, 5.0e5),
     "config3_kappa": (2 * 256**3, 50000, 142.2, 5.0e5),
     "config3_iter": (2 * 256**3, 50000, 142.2, 5.0e5),  # + the iterative inertia tensors (20 passes)
+    # BASELINE config 4: COLIBRE_THERMAL-like hydro chunk, projected apertures {1,3,10,30,50,100} kpc with
+    # projected dispersions / half-mass radii / tensors + ExclusiveSphere 3-D kinematics, tensors, half-mass radii
+    "config4": (2 * 376**3, 50000, 25.0, 2.0e5),
 }
+# particle mass (1e10 Msun) where it differs from the config-2 recipe: config 4 keeps config 2's mean density
+M_PART = {"config4": 0.0843 * (25.0 / 284.4) ** 3 * 512**3 / (2 * 376**3)}
 HYDRO_TYPES = {0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001}
 SEED = 20261018
 SO_LIST = None  # filled in main (needs synth)
+CPU_SAMPLE_FRACTION = 0.05  # volume fraction of the fixed central sub-cube the CPU arm processes
 
-# algorithmic bytes per unit of each kernel phase (DESIGN.md "Kernels")
-ALG_BYTES = {
-    "mesh": 32,      # per particle: read 24 B position, write 4 B key + 4 B permutation
-    "count": 28,     # per in-sphere particle of the rung: position 24 + mass 4
-    "collect": 49,   # per gathered particle: position 24 + mass 4 + grnr 4 + type 1 + 16 B record out
-    "sort": 32,      # per record: 16 B in + 16 B out
-    "scan_solve": 16,  # per record (one read of the sorted profile)
-    "moments": 48,   # per pair: position 24, mass 4, velocity 12, grnr 4, fof 4
-    # fused tiers (small.cu), per pair: the whole stage B+C figure of SURVEY.md 8(d)
-    "tier_0": 48, "tier_1": 48,
+# Algorithmic bytes per unit of every kernel.  unit = which counter the kernel's work is
+# proportional to: "part" particles of the chunk, "tier0"/"tier1" final pairs of the staged tiers, "tier" both,
+# "count" in-sphere particles of the count sweeps, "rec" records gathered on the general path, "mom" pairs of the
+# general moment sweeps, "halo" halos.  Re-reads, out-of-sphere candidates and retried rungs are not credited.
+KERNEL_MODEL = {
+    "k_bounds_partial": (24, "part"),      # positions in
+    "k_cell_keys": (32, "part"),           # 24 position in, 4 key + 4 index out
+    "k_rs_hist": (4, "part"),              # per pass: keys in
+    "k_rs_scatter": (16, "part"),          # per pass: 8 in, 8 out
+    "k_cell_offsets": (4, "part"),
+    "k_gather": (102, "part"),             # 4 permutation + 49 payload in, 49 out
+    "k_tier_front<256>": (57, "tier0"),    # 24 position + 4 mass + 4 grnr + 4 fof + 1 type in, 16 record + 4 slot out
+    "k_tier_front<1024>": (57, "tier1"),
+    "k_solve_seq": (16, "tier"),           # one read of the sorted records
+    "k_tier_moments": (52, "tier"),        # 4 slot + 48 payload
+    "k_rows": (None, "halo"),              # ncol * 8 out, filled in at run time
+    "k_count": (28, "count"),              # position 24 + mass 4
+    "k_fine_hist_halo": (24, "rec"),
+    "k_collect": (49, "rec"),              # 33 in, 16 record out
+    "k_sort_bins": (32, "rec"),            # 16 in, 16 out
+    "k_scan_solve": (16, "rec"),
+    "k_moments": (48, "mom"),              # position 24, mass 4, velocity 12, grnr 4, fof 4
+    "k_projected": (48, "mom"),
+    "k_kappa": (48, "mom"),
+    "k_it_accum": (41, "mom"),
 }
+
+
+def kernel_key(name):
+    """normalise a launch-site name ("(k_moments<V_FULL, 4>)") to its KERNEL_MODEL key"""
+    n = name.strip("() ")
+    if n in KERNEL_MODEL:
+        return n
+    return n.split("<")[0]
 
 
 def log(*a):
@@ -145,9 +174,10 @@ def _cpu_worker(args):
     (mirrors the fetch-and-add loop of SOAP/core/halo_tasks.py:342-357)."""
     from oracle import halo as oh
 
-    counter, n_h = args
+    counter, n_h, keep = args
     data, H, meshes, props, params, td = (_G[k] for k in ("data", "H", "meshes", "props", "params", "td"))
     done = pairs = 0
+    rows = []
     while True:
         with counter.get_lock():
             i = counter.value
@@ -157,16 +187,22 @@ def _cpu_worker(args):
         ih = {k: (v[i].copy() if v.ndim > 1 else v[i]) for k, v in H.items()}
         try:
             res, info = oh.process_single_halo(meshes, data, props, params, ih, td if ih["is_central"] == 1 else None)
-        except RuntimeError:
-            res, info = None, {}
+            err = None
+        except RuntimeError as e:
+            res, info, err = None, {"n_loop": -1}, str(e)
         done += 1
         if res is not None:
             pairs += sum(len(v) for v in info["idx"].values())
-    return done, pairs
+        if keep:
+            if res is not None:
+                info = dict(info, idx={t: np.empty(len(v), dtype=np.int8) for t, v in info["idx"].items()})  # lengths only
+            rows.append((i, res, info, ih, err))
+    return done, pairs, rows
 
 
-def cpu_reference_pass(sample, cp, so_list, cores):
-    """Stage A (mesh build) + stage B/C (halo loop) of the oracle on the host."""
+def cpu_reference_pass(sample, cp, so_list, cores, keep=False, faithful=True):
+    """Stage A (mesh build) + stage B/C (halo loop) of the oracle on the host.  keep: also return the per-halo
+    oracle results (for the parity summary of the bench line)."""
     from oracle import halo as oh
     from oracle import mesh as om
     from tests import _compare as cmp
@@ -175,7 +211,7 @@ def cpu_reference_pass(sample, cp, so_list, cores):
     t0 = time.time()
     meshes = {t: om.MeshOracle(d["Coordinates"], om.mesh_resolution(len(d["Masses"]))) for t, d in data.items()}
     t_mesh = time.time() - t0
-    params = cmp.oracle_params(cp, faithful=True)
+    params = cmp.oracle_params(cp, faithful=faithful)
     props = cmp.oracle_prop_list(params, cp, so_list, [])
     td = oh.target_density_of(props, params)
     _G.update(data=data, H=H, meshes=meshes, props=props, params=params, td=td)
@@ -185,7 +221,7 @@ def cpu_reference_pass(sample, cp, so_list, cores):
     q = ctx.Queue()
 
     def run(counter, n_h, q):
-        q.put(_cpu_worker((counter, n_h)))
+        q.put(_cpu_worker((counter, n_h, keep)))
 
     procs = [ctx.Process(target=run, args=(counter, n_h, q)) for _ in range(cores)]
     t0 = time.time()
@@ -197,39 +233,78 @@ def cpu_reference_pass(sample, cp, so_list, cores):
     t_halo = time.time() - t0
     done = sum(r[0] for r in res)
     pairs = sum(r[1] for r in res)
-    return dict(t_mesh=t_mesh, t_halo=t_halo, halos=done, pairs=pairs)
+    rows = sorted((x for r in res for x in r[2]), key=lambda x: x[0])
+    return dict(t_mesh=t_mesh, t_halo=t_halo, halos=done, pairs=pairs, rows=rows, props=props)
 
 
-def make_sample(data_np, H_np, L, n_target):
-    """Bounded sub-chunk of the workload: halos whose centre lies in a central
-    sub-cube, with every particle within that cube + a ghost shell of one
-    maximum read radius (how SOAP itself cuts chunks: SURVEY.md 8(e))."""
-    n_h = len(H_np["index"])
-    frac = min(1.0, n_target / max(n_h, 1))
+def make_sample(data_np, H_np, L, frac=CPU_SAMPLE_FRACTION, margin=6.0):
+    """The CPU arm's bounded sample, fixed by the workload alone (no timing pilot): every halo whose centre lies
+    in the central sub-cube holding ``frac`` of the volume and whose read radius fits in the ghost shell, with
+    every particle within that cube + a shell of ``margin`` (how SOAP itself cuts chunks: SURVEY.md 8(e)).
+    Returns the sub-chunk, the indices of its halos in the full list, and how many halos of the cube were left
+    out because their read radius exceeds the shell."""
     side = L * frac ** (1.0 / 3.0)
-    margin = 6.0
     lo, hi = 0.5 * L - 0.5 * side, 0.5 * L + 0.5 * side
     c = H_np["cofp"]
-    hsel = np.all((c >= lo) & (c < hi), axis=1) & (H_np["read_radius"] <= margin)
+    in_cube = np.all((c >= lo) & (c < hi), axis=1)
+    hsel = in_cube & (H_np["read_radius"] <= margin)
     Hs = {k: v[hsel] for k, v in H_np.items()}
     ds = {}
     for t, d in data_np.items():
         p = d["Coordinates"]
         psel = np.all((p >= lo - margin) & (p < hi + margin), axis=1)
         ds[t] = {k: np.ascontiguousarray(v[psel]) for k, v in d.items()}
-    return ds, Hs, side, margin
+    return ds, Hs, side, margin, np.flatnonzero(hsel), int(in_cube.sum() - hsel.sum())
 
 
-def size_sample_and_time(data_np, H_np, L, cp, so_list, cores, budget_s):
-    """Pilot on a small sub-chunk, then size the timed sub-chunk to ~budget_s."""
-    ds, Hs, _, _ = make_sample(data_np, H_np, L, 40 * cores)
-    if len(Hs["index"]) == 0:
-        ds, Hs, _, _ = make_sample(data_np, H_np, L, len(H_np["index"]))
-    pilot = cpu_reference_pass((ds, Hs), cp, so_list, cores)
-    rate = pilot["halos"] / max(pilot["t_mesh"] + pilot["t_halo"], 1e-3)
-    n_target = int(max(40 * cores, min(len(H_np["index"]), rate * budget_s)))
-    sample = make_sample(data_np, H_np, L, n_target)
-    return sample
+def sample_description(ds, Hs, side, margin, dropped, cores):
+    return (f"fixed central sub-cube holding {100 * CPU_SAMPLE_FRACTION:.0f} % of the volume (side {side:.1f} Mpc) + "
+            f"{margin} Mpc ghost shell: {len(Hs['index'])} halos ({dropped} more left out: read radius > shell), "
+            f"{sum(len(d['Masses']) for d in ds.values())} particles; mesh build + halo loop, numpy oracle port, "
+            f"{cores} processes pulling halos largest-first")
+
+
+def parity_summary(res, r, hidx, cp, faithful):
+    """GPU table of the timed step vs oracle rows of the same halos of the same chunk."""
+    from tests import _compare as cmp
+
+    rows = r["rows"]
+    oracle_out = [(x[1], x[2], x[3], x[4]) for x in rows]
+    halos = [int(hidx[x[0]]) for x in rows]
+    rep = cmp.compare(res, oracle_out, r["props"], cp, halos=halos, flags=8, faithful=faithful)
+    m = rep.maxerr
+    for b in rep.bad[:10]:
+        log("[bench] parity: out of tolerance:", b)
+    int_keys = ("Ngas", "Ndm", "Nstar", "Nbh", "n_pairs")
+    mr_keys = ("r", "Mso", "Mtot", "Mdm", "HalfMassRadiusTot", "HalfMassRadiusDM", "EncloseRadius", "R_vmax_soft", "R_vmax_unsoft",
+               "Mfrac_satellites", "Mfrac_external", "Vmax_soft", "Vmax_unsoft")
+    return {
+        "halos": len(halos), "counts_exact": all(m.get(k, 0.0) == 0.0 for k in int_keys),
+        "n_loop_exact": m.get("n_loop", 0.0) == 0.0, "radius_exact": m.get("radius", 0.0) <= 1e-15,
+        "max_rel_mass_radius": max(m.get(k, 0.0) for k in mr_keys),
+        "max_rel_second_moment": max(m.get(k, 0.0) for k in ("spin_parameter", "concentration_soft", "concentration_unsoft",
+                                                             "concentration_dmo_soft", "concentration_dmo_unsoft")),
+        "out_of_tolerance": len(rep.bad),
+        "worst_keys": {k: float(f"{v:.3g}") for k, v in sorted(m.items(), key=lambda kv: -kv[1])[:5]},
+    }
+
+
+def parity_block(res, sample, hidx, cp, so_list, cores, r_faithful):
+    """The bench line's parity field.  ``float64``: the oracle with every sum in float64 on >= 2000 halos of the
+    sample including its 50 largest -- north_star's tolerances (1e-6 masses / radii, 1e-4 second moments).
+    ``faithful``: the rows of the timed CPU run (reference dtypes: float32 sums and a float32 cumsum in get_vmax,
+    kinematic_properties.py:583, whose argmax can land on another particle), reported for reference."""
+    ds, Hs = sample
+    n = len(Hs["index"])
+    order = np.argsort(-Hs["nr_bound_part"], kind="stable")
+    pick = np.unique(np.concatenate([order[:50], np.arange(0, n, max(1, n // 2000))]))
+    Hp = {k: v[pick] for k, v in Hs.items()}
+    r64 = cpu_reference_pass((ds, Hp), cp, so_list, cores, keep=True, faithful=False)
+    out = {"against": "numpy oracle on the CPU sample of the chunk of the timed step",
+           "float64": parity_summary(res, r64, hidx[pick], cp, faithful=False)}
+    if r_faithful is not None:
+        out["faithful"] = parity_summary(res, r_faithful, hidx, cp, faithful=True)
+    return out
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -238,22 +313,25 @@ def size_sample_and_time(data_np, H_np, L, cp, so_list, cores, budget_s):
 def build_config(cp, so_list, workload="config2"):
     from soap_b200.halo_tasks import HaloPropConfig, PF_HMR, PF_ITER, PF_KAPPA, PF_KIN, PF_TENS
 
+    common = dict(
+        boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
+        mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
+        H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
+        nu_density=cp["nu_density"], phys_mpc_to_coord=cp["phys_mpc_to_coord"], do_subhalo=True)
     if workload.startswith("config3"):
         aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, incl) for kpc in (30.0, 50.0, 100.0) for incl in (0, 1)]
         flags = PF_KIN | PF_TENS | PF_HMR | (PF_KAPPA if workload.endswith("kappa") else 0) | \
             (PF_ITER if workload.endswith("iter") else 0)
-        return HaloPropConfig(
-            boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
-            mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
-            H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
-            nu_density=cp["nu_density"], phys_mpc_to_coord=cp["phys_mpc_to_coord"],
-            do_subhalo=True, so=list(so_list), apertures=aps, property_flags=flags, dmo=False)
-    return HaloPropConfig(
-        boxsize=cp["boxsize"], G=cp["G"], critical_density=cp["critical_density"],
-        mean_density=cp["mean_density"], softening={t: cp["softening"] for t in (0, 1, 4, 5)},
-        H=cp["H"], kpc_per_length=cp["kpc_per_length"], r_20mpc=cp["r_20mpc"],
-        nu_density=cp["nu_density"], phys_mpc_to_coord=cp["phys_mpc_to_coord"],
-        do_subhalo=True, so=list(so_list), apertures=[], property_flags=PF_HMR, dmo=True)
+        return HaloPropConfig(so=list(so_list), apertures=aps, property_flags=flags, dmo=False, **common)
+    if workload == "config4":
+        # parameter_files/COLIBRE_THERMAL.yml: ProjectedApertureProperties variations 1..100 kpc, ExclusiveSphere
+        # kinematics / tensors / half-mass radii
+        radii = (1.0, 3.0, 10.0, 30.0, 50.0, 100.0)
+        proj = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3) for kpc in radii]
+        aps = [(kpc * 1e-3 * cp["phys_mpc_to_coord"], kpc * 1e-3, 0) for kpc in radii]
+        return HaloPropConfig(so=[], apertures=aps, projected=proj, property_flags=PF_KIN | PF_TENS | PF_HMR, dmo=False,
+                              skip_gt=("exclusive",), **common)
+    return HaloPropConfig(so=list(so_list), apertures=[], property_flags=PF_HMR, dmo=True, **common)
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -327,7 +405,11 @@ def main():
     so_list = [("crit", 200.0), ("mean", 200.0), ("crit", 500.0), ("BN98", float(synth.virBN98()))]
     n_part, n_halos, L, max_np = WORKLOADS[args.workload]
     cp = synth.coordinate_unit_params(L)
-    if args.workload.startswith("config3"):
+    if args.workload == "config4":
+        wl_name = (f"{args.workload}: synthetic COLIBRE_THERMAL-like hydro chunk (gas/DM/stars/BH), {n_part} particles, "
+                   f"{n_halos} halos, L={L} Mpc, projected apertures 1/3/10/30/50/100 kpc (3 axes: masses, dispersions, "
+                   "half-mass radii, tensors) + ExclusiveSphere kinematics, tensors, half-mass radii + BoundSubhalo")
+    elif args.workload.startswith("config3"):
         wl_name = (f"{args.workload}: synthetic hydro chunk (gas/DM/stars/BH), {n_part} particles, {n_halos} halos, "
                    f"L={L} Mpc, exclusive+inclusive 30/50/100 kpc apertures + SO x4 + BoundSubhalo, kinematics, "
                    "tensors, half-mass radii")
@@ -342,9 +424,10 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank) if (have_cuda and world > 1 and args.impl == "ours") else None
 
     t0 = time.time()
-    hydro = args.workload.startswith("config3")
-    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank + (1 if hydro else 0), device=gen_dev, max_np=max_np,
-                                  type_fractions=HYDRO_TYPES if hydro else None)
+    hydro = args.workload.startswith("config3") or args.workload == "config4"
+    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank + (1 if hydro else 0) + (1 if args.workload == "config4" else 0),
+                                  device=gen_dev, max_np=max_np, type_fractions=HYDRO_TYPES if hydro else None,
+                                  **({"m_part": M_PART[args.workload]} if args.workload in M_PART else {}))
     if have_cuda:
         torch.cuda.synchronize()
     log(f"[bench] rank {rank}: generated {args.workload} on {gen_dev} in {time.time() - t0:.1f}s")
@@ -353,9 +436,7 @@ def main():
     if args.impl == "reference":
         data_np, H_np = synth.to_numpy(data, halos)
         del data, halos
-        budget = max(3.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
-        sample = size_sample_and_time(data_np, H_np, L, cp, so_list, cores, budget)
-        ds, Hs, side, margin = sample
+        ds, Hs, side, margin, hidx, dropped = make_sample(data_np, H_np, L)
         n_s = len(Hs["index"])
         times, pairs = [], 0
         for it in range(args.warmup + args.steps):
@@ -365,9 +446,7 @@ def main():
                 pairs = r["pairs"]
         t = float(np.mean(times)) if times else float("nan")
         val = n_s / t
-        sample_desc = (f"central sub-cube of side {side:.1f} Mpc + {margin} Mpc ghost shell: {n_s} halos, "
-                       f"{sum(len(d['Masses']) for d in ds.values())} particles; mesh build + halo loop, "
-                       f"{cores} processes pulling halos largest-first")
+        sample_desc = sample_description(ds, Hs, side, margin, dropped, cores)
         out = {
             "impl": "reference", "metric": "halos_per_s", "value": val, "unit": "halos/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
@@ -398,30 +477,45 @@ def main():
     ncol, cols = result_layout(cfg.to_c())
     H = int(halos["cofp"].shape[0])
     table = torch.empty((H, ncol), dtype=torch.float64, device=dev)
-    gather_buf = [torch.empty_like(table) for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Results stay per rank ("each rank appends to its own ResultSet"); what NCCL moves is a float32
+    # copy of the table (PropertyTable's output precision) gathered to rank 0 asynchronously, overlapped with the
+    # next chunk's kernels and waited for before the timed region ends.
+    gather32 = [torch.empty((H, ncol), dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    send32 = torch.empty((H, ncol), dtype=torch.float32, device=dev) if world > 1 else None
+    pending = []
+
     def step_device():
         chunk = DeviceChunk(data, L, device=local_rank, fine_ppc=args.fine_ppc, handle=handle)
         res = process_halos(chunk, cfg, halos, out=table)
         if world > 1:
-            dist.gather(table, gather_buf, dst=0)
+            for w in pending:
+                w.wait()
+            pending.clear()
+            send32.copy_(table)
+            pending.append(dist.gather(send32, gather32, dst=0, async_op=True))
         return chunk, res
 
     # warm-up
     for _ in range(max(args.warmup, 0)):
         chunk, res = step_device()
         chunk.free()
+    for w in pending:
+        w.wait()
+    pending.clear()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     phases = {}
     stats = {}
     l0 = handle.launches()
+    handle.kernel_timings()  # drop what the warm-up left
+    handle.kernel_timing(True)  # CUDA events around every launch, on the launching stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -433,9 +527,14 @@ def main():
             else:
                 phases[k] = phases.get(k, 0.0) + v
         chunk.free()
+    for w in pending:
+        w.wait()
+    pending.clear()
     ev1.record()
     barrier()
     clocks = sampler.stop()
+    handle.kernel_timing(False)
+    ktimes = handle.kernel_timings()
     launches = handle.launches() - l0
     ms = ev0.elapsed_time(ev1) / max(args.steps, 1)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -501,56 +600,69 @@ def main():
                "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i", "numa_node": numa}
 
     # -------------------------------------------------------- roofline (rank 0)
+    # per kernel: launches and device time from the CUDA events the library records around every launch of the
+    # timed region; achieved = algorithmic bytes of those launches / their time (KERNEL_MODEL)
     peak, peak_kind = peak_hbm()
     steps = max(args.steps, 1)
     ph = {k: v / steps for k, v in phases.items()}  # ms per step
-    mesh_ms = sum(v for k, v in ph.items() if k.startswith("create/"))
-    units = {
-        "mesh": (n_part, mesh_ms),
-        "count": (stats.get("count_pairs", 0.0), ph.get("halos/count", 0.0)),
-        "collect": (stats.get("try_pairs", 0.0), ph.get("halos/collect", 0.0) + ph.get("halos/fine_hist", 0.0)),
-        "sort": (stats.get("try_pairs", 0.0), ph.get("halos/sort", 0.0)),
-        "scan_solve": (stats.get("try_pairs", 0.0), ph.get("halos/scan_solve", 0.0)),
-        "moments": (stats.get("moment_pairs", 0.0), ph.get("halos/moments", 0.0)),
-        "tier_0": (stats.get("small_pairs_0", 0.0), ph.get("halos/tier_0", 0.0)),
-        "tier_1": (stats.get("small_pairs_1", 0.0), ph.get("halos/tier_1", 0.0)),
+    unit_count = {
+        "part": float(n_part), "tier0": stats.get("small_pairs_0", 0.0), "tier1": stats.get("small_pairs_1", 0.0),
+        "tier": stats.get("small_pairs", 0.0), "count": stats.get("count_pairs", 0.0), "rec": stats.get("try_pairs", 0.0),
+        "mom": stats.get("moment_pairs", 0.0), "halo": float(H),
     }
     kernels = {}
-    for k, (n_units, t_ms) in units.items():
-        gbs = ALG_BYTES[k] * n_units / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
-        kernels[k] = {"ms": round(t_ms, 4), "units": int(n_units), "alg_bytes_per_unit": ALG_BYTES[k],
-                      "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 4)}
-    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    for name, (n_l, t_ms) in ktimes.items():
+        key = kernel_key(name)
+        e = kernels.setdefault(key, {"launches_per_step": 0.0, "ms": 0.0})
+        e["launches_per_step"] += n_l / steps
+        e["ms"] += t_ms / steps
+    for key, e in kernels.items():
+        bpu, unit = KERNEL_MODEL.get(key, (None, None))
+        if key == "k_rows":
+            bpu = 8.0 * ncol
+        e["ms"] = round(e["ms"], 4)
+        e["launches_per_step"] = round(e["launches_per_step"], 2)
+        if bpu is None:
+            continue
+        n_units = unit_count[unit]
+        # kernels launched once per pass over the data (radix passes) process the units once per launch
+        per_launch = key in ("k_rs_hist", "k_rs_scatter", "k_bounds_partial")
+        total_bytes = bpu * n_units * (e["launches_per_step"] if per_launch else 1.0)
+        gbs = total_bytes / (e["ms"] * 1e-3) / 1e9 if e["ms"] > 0 else 0.0
+        e.update(alg_bytes_per_unit=bpu, unit=unit, units_per_step=int(n_units), achieved_gbs=round(gbs, 2),
+                 frac=round(gbs / peak, 4))
+    modelled = {k: v for k, v in kernels.items() if "frac" in v}
+    dom = max(modelled, key=lambda k: modelled[k]["ms"])
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")))
         traffic = tr.get(args.workload, {}).get(dom)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic,
-                "launches_per_step": 1 if dom.startswith("tier") or dom == "mesh" else int(stats.get("rounds", 1))}
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": modelled[dom]["achieved_gbs"], "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": modelled[dom]["frac"], "traffic": traffic,
+                "launches_per_step": modelled[dom]["launches_per_step"], "ms_per_step": modelled[dom]["ms"],
+                "share_of_step": round(modelled[dom]["ms"] / ms_step, 3)}
     total_alg = 32.0 * n_part + 48.0 * pairs + 8.0 * H * ncol
     kern_ms = sum(v["ms"] for v in kernels.values())
 
-    # -------------------------------------------------------- cpu baseline
+    # -------------------------------------------------------- cpu baseline + parity (rank 0)
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline and not hydro:
         try:
             src = host if not args.no_e2e else {t: {k: v.cpu() for k, v in d.items()} for t, d in data.items()}
             data_np = {t: {k: v.numpy() for k, v in d.items()} for t, d in src.items()}
             H_np = {k: v.cpu().numpy() for k, v in halos.items()}
-            ds, Hs, side, margin = size_sample_and_time(data_np, H_np, L, cp, so_list, cores, args.cpu_budget)
-            r = cpu_reference_pass((ds, Hs), cp, so_list, cores)
+            ds, Hs, side, margin, hidx, dropped = make_sample(data_np, H_np, L)
+            r = cpu_reference_pass((ds, Hs), cp, so_list, cores, keep=True)
             t = r["t_mesh"] + r["t_halo"]
             cpu_baseline = {
                 "value": r["halos"] / t, "unit": "halos/s", "cores": cores, "kind": "port",
-                "pairs_per_s": r["pairs"] / t,
-                "sample": (f"central sub-cube of side {side:.1f} Mpc + {margin} Mpc ghost shell: {r['halos']} halos, "
-                           f"{sum(len(d['Masses']) for d in ds.values())} particles, {t:.1f} s "
-                           f"(mesh {r['t_mesh']:.1f} s + halo loop {r['t_halo']:.1f} s), numpy oracle port, "
-                           f"{cores} processes pulling halos largest-first"),
+                "pairs_per_s": r["pairs"] / t, "seconds": round(t, 2),
+                "sample": sample_description(ds, Hs, side, margin, dropped, cores),
             }
+            parity = parity_block(res, (ds, Hs), hidx, cp, so_list, cores, r)
         except Exception as e:  # the baseline is reported, never required
             cpu_baseline = {"value": None, "unit": "halos/s", "cores": cores, "kind": "port", "sample": f"failed: {e!r}"}
 
@@ -563,14 +675,16 @@ def main():
             "config": {"workload": wl_name, "l2": "inputs (48 B x particles) larger than L2; no flush needed",
                        "halos_ok": n_ok, "halos": H, "internal_mesh_res": int(stats.get("res", 0)),
                        "ladder_rounds": int(stats.get("rounds", 0)), "ncol": ncol,
-                       "parallelism": f"{world} independent chunks, one per GPU; NCCL gather of result tables"},
+                       "parallelism": f"{world} chunks, one per GPU, no data-path collective; float32 result tables gathered to "
+                                      "rank 0 over NCCL asynchronously (overlapped with the next chunk)"},
             "pairs_per_s": pairs * world / (ms_step * 1e-3), "pairs_per_step": int(pairs),
             "candidates_per_step": int(stats.get("candidates", 0)),
             "algorithmic_gbs_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9 / peak, 4),
             "kernel_ms_per_step": round(kern_ms, 3),
             "roofline": roofline, "kernels": kernels, "phases_ms": {k: round(v, 4) for k, v in sorted(ph.items())},
-            "stats": {k: int(v) for k, v in sorted(stats.items())}, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "stats": {k: int(v) for k, v in sorted(stats.items())}, "cpu_baseline": cpu_baseline, "parity": parity,
+            "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(out)

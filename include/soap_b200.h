@@ -55,6 +55,11 @@ int soap_create(int device, soap_handle** out);
 int soap_destroy(soap_handle* h);
 /* number of kernels launched through this handle so far (bench.py gpu_launches) */
 int64_t soap_launch_count(const soap_handle* h);
+/* per-kernel device time: with timing on, every launch through the handle is bracketed by CUDA events on its
+ * stream; soap_kernel_timings synchronises the device, writes "kernel name\tlaunches\tmilliseconds\n" lines for
+ * everything launched since the last call and returns the number of bytes (bench.py's roofline line) */
+int soap_kernel_timing(soap_handle* h, int on);
+int64_t soap_kernel_timings(soap_handle* h, char* buf, int64_t buflen);
 
 /* ------------------------------------------------------------------ stage A */
 /* box_wrap: SOAP/core/chunk_tasks.py:48-50 (numpy floored modulo), in place. */

@@ -97,6 +97,8 @@ SYMBOLS = {
     "soap_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "soap_destroy": (C.c_int, [C.c_void_p]),
     "soap_launch_count": (C.c_int64, [C.c_void_p]),
+    "soap_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "soap_kernel_timings": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
     "soap_box_wrap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_void_p]),
     "soap_mesh_build": (
         C.c_int,
@@ -166,6 +168,20 @@ class Handle:
 
     def launches(self):
         return int(lib().soap_launch_count(self.ptr))
+
+    def kernel_timing(self, on=True):
+        check(lib().soap_kernel_timing(self.ptr, int(bool(on))))
+
+    def kernel_timings(self):
+        """{kernel name: (launches, total ms)} since the last call (synchronises the device)"""
+        buf = C.create_string_buffer(1 << 16)
+        lib().soap_kernel_timings(self.ptr, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().strip().split("\n"):
+            if line:
+                name, n, ms = line.split("\t")
+                out[name] = (int(n), float(ms))
+        return out
 
     def close(self):
         if self.ptr:

@@ -42,10 +42,51 @@ struct PhaseTimer {
     float ms = 0.f;
 };
 
+// Per-kernel device time (CUDA events on the launching stream around every launch), switched on by
+// soap_kernel_timing(): what bench.py's roofline line is computed from.
+struct KernelLog {
+    struct Span { const char* name; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    std::map<std::string, std::pair<int64_t, double>> acc;  // name -> (launches, ms)
+    cudaEvent_t ev() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(const char* name, cudaStream_t s) {
+        Span sp{name, ev(), ev()};
+        cudaEventRecord(sp.e0, s);
+        spans.push_back(sp);
+    }
+    void end(cudaStream_t s) { cudaEventRecord(spans.back().e1, s); }
+    // call after the streams have been synchronised
+    void collect() {
+        for (auto& sp : spans) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) {
+                auto& a = acc[sp.name];
+                a.first += 1;
+                a.second += t;
+            } else {
+                cudaGetLastError();
+            }
+            pool.push_back(sp.e0);
+            pool.push_back(sp.e1);
+        }
+        spans.clear();
+    }
+    ~KernelLog() {
+        for (auto& sp : spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
 struct soap_handle {
     int device = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    bool ktime = false;
+    KernelLog klog;
     std::map<std::string, WsBuf> ws;
     // returns nullptr on failure (error string set)
     void* get(const char* name, size_t bytes) {
@@ -83,15 +124,19 @@ struct soap_handle {
     type* var = (type*)(handle)->get(name, sizeof(type) * (size_t)(count)); \
     if (!var) return -1;
 
-#define LAUNCH(h, kernel, grid, block, smem, stream, ...)                         \
+#define LAUNCH_N(h, name, kernel, grid, block, smem, stream, ...)                 \
     do {                                                                          \
+        if ((h)->ktime) (h)->klog.begin(name, stream);                            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+        if ((h)->ktime) (h)->klog.end(stream);                                    \
         (h)->launches++;                                                          \
         cudaError_t _e = cudaGetLastError();                                      \
         if (_e != cudaSuccess)                                                    \
-            SOAP_FAIL("%s:%d launch %s -> %s", __FILE__, __LINE__, #kernel,       \
+            SOAP_FAIL("%s:%d launch %s -> %s", __FILE__, __LINE__, name,          \
                       cudaGetErrorString(_e));                                    \
     } while (0)
+#define LAUNCH(h, kernel, grid, block, smem, stream, ...) \
+    LAUNCH_N(h, #kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {
     int64_t g = (n + block - 1) / block;

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(PLAN_NT) k_plan_items(ChunkView v, HaloArrays 
 // the sphere of the furthest rung is swept once and every particle is binned by
 // the first rung whose radius includes it (the same r2 <= radius^2 test).
 __global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
-                                              Counters* ctr) {
+                                              Counters* ctr, double* __restrict__ item_msum) {
     __shared__ SweepShared S;
     __shared__ unsigned int s_cnt[TB / 32][LOOK_MAX];
     __shared__ double s_m[TB / 32][LOOK_MAX];
@@ -282,13 +282,16 @@ __global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, con
             if (lane == 0) { s_cnt[wid][k] = c; s_m[wid][k] = m; }
         }
         __syncthreads();
+        if (threadIdx.x < LOOK_MAX && threadIdx.x >= (unsigned)nr) item_msum[(size_t)it * LOOK_MAX + threadIdx.x] = 0.0;
         if (threadIdx.x < (unsigned)nr) {
             const int k = threadIdx.x;
             unsigned int c = 0;
             double m = 0.0;
             for (int w = 0; w < TB / 32; w++) { c += s_cnt[w][k]; m += s_m[w][k]; }
             if (c) atomicAdd(&ha.rung_cnt[(size_t)h * LOOK_MAX + k], c);
-            if (m != 0.0) atomicAdd(&ha.rung_msum[(size_t)h * LOOK_MAX + k], m);
+            // the mass of a rung is summed over the halo's work items in item order by k_gate: the same chunk
+            // gives the same float64 sum, hence the same density gate decision, on every run
+            item_msum[(size_t)it * LOOK_MAX + k] = m;
             atomicAdd(&ctr->count_pairs, (unsigned long long)c);
         }
         __syncthreads();
@@ -302,7 +305,8 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
                                               uint32_t* __restrict__ acc_list,
                                               uint32_t* __restrict__ multi_list,
                                               uint32_t* __restrict__ seq_list,
-                                              uint32_t* __restrict__ next, Counters* ctr) {
+                                              uint32_t* __restrict__ next, Counters* ctr,
+                                              const double* __restrict__ item_msum) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= *n_pend) return;
     const uint32_t h = pend[it];
@@ -316,7 +320,12 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
         ha.nloop[h] += 1;  // halo_tasks.py:75
         const double r = ha.cur_r[h];
         ccum += ha.rung_cnt[(size_t)h * LOOK_MAX + k];
-        mcum += ha.rung_msum[(size_t)h * LOOK_MAX + k];
+        {
+            const uint32_t ib = ha.item_base[h], ni = ha.n_items[h];
+            double mk = 0.0;
+            for (uint32_t j = 0; j < ni; j++) mk += item_msum[(size_t)(ib + j) * LOOK_MAX + k];
+            mcum += mk;
+        }
         // halo_tasks.py:97
         const double density = mcum / (4.0 / 3.0 * SOAP_PI * (r * r * r));
         if (!has_target || density <= cfg.target_density) {  // halo_tasks.py:103
@@ -985,6 +994,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(items, Item, h, "h_items", items_cap);
     WS_GET(item_minr, unsigned long long, h, "h_item_minr", items_cap);
     WS_GET(item_minfof, int32_t, h, "h_item_minfof", items_cap);
+    WS_GET(item_msum, double, h, "h_item_msum", items_cap * LOOK_MAX);
 
     PhaseLog& log = c->halo_log;
     log.reset();
@@ -1083,7 +1093,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             items = (Item*)h->get("h_items", sizeof(Item) * items_cap);
             item_minr = (unsigned long long*)h->get("h_item_minr", sizeof(unsigned long long) * items_cap);
             item_minfof = (int32_t*)h->get("h_item_minfof", sizeof(int32_t) * items_cap);
-            if (!items || !item_minr || !item_minfof) return -1;
+            item_msum = (double*)h->get("h_item_msum", sizeof(double) * items_cap * LOOK_MAX);
+            if (!items || !item_minr || !item_minfof || !item_msum) return -1;
             if (!replan) CUDA_TRY(cudaMemsetAsync(&ctr->candidates, 0, sizeof(unsigned long long), stream));
         }
         return 0;
@@ -1098,11 +1109,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         if (plan(pend, n_pend_dev, n_pend, look, 0)) return -1;
         log.end(stream);
         log.begin("count", stream);
-        LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr);
+        LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr, item_msum);
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
-               acc_list, multi_list, seq_list, next, ctr);
+               acc_list, multi_list, seq_list, next, ctr, item_msum);
         log.end(stream);
         Counters hc;
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));

@@ -272,6 +272,30 @@ int soap_destroy(soap_handle* h) {
 
 int64_t soap_launch_count(const soap_handle* h) { return h ? h->launches : 0; }
 
+int soap_kernel_timing(soap_handle* h, int on) {
+    if (!h) SOAP_FAIL("soap_kernel_timing: NULL handle");
+    h->ktime = on != 0;
+    return 0;
+}
+
+int64_t soap_kernel_timings(soap_handle* h, char* buf, int64_t buflen) {
+    if (!h || !buf || buflen <= 0) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->klog.collect();
+    std::string s;
+    char line[512];
+    for (auto& kv : h->klog.acc) {
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+        s += line;
+    }
+    h->klog.acc.clear();
+    const int64_t m = (int64_t)s.size() < buflen - 1 ? (int64_t)s.size() : buflen - 1;
+    memcpy(buf, s.data(), m);
+    buf[m] = 0;
+    return m;
+}
+
 int soap_box_wrap(soap_handle* h, double* pos_dev, int64_t n, const double ref_pos[3],
                   double boxsize, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

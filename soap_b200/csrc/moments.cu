@@ -119,6 +119,27 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
     }
 }
 
+// Banks of the halos of `list` -> cumulative over radial shells, in place: a selection is a prefix of the shells,
+// so the row writer then reads one shell instead of summing up to a dozen.  One thread per (halo, bank column).
+__global__ void __launch_bounds__(128) k_bank_prefix(HaloArrays ha, const uint32_t* __restrict__ list,
+                                                     const unsigned int* __restrict__ n_list, int per_shell) {
+    const unsigned int it = blockIdx.y;
+    for (unsigned int hi = it; hi < *n_list; hi += gridDim.y) {
+        const uint32_t h = list[hi];
+        const int c_lo = ha.commit_lo[h], c_hi = ha.commit_hi[h];
+        if (c_hi <= c_lo || ha.status[h] >= 2) continue;
+        const int nshell = ha.cuts[h].n + 1;
+        double* b = ha.gbank + ha.bank_off[h];
+        for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < per_shell; col += gridDim.x * blockDim.x) {
+            double run = b[col];
+            for (int s = 1; s < nshell; s++) {
+                run += b[(size_t)s * per_shell + col];
+                b[(size_t)s * per_shell + col] = run;
+            }
+        }
+    }
+}
+
 // Result rows: one thread per (halo, selection) -- BoundSubhalo, each SO, each aperture.  The
 // selections of a warp are the same, so the row writer's branches do not diverge.
 struct SelIds {
@@ -222,6 +243,11 @@ int soap_launch_rows(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, con
     for (int q = 0; q < cfg.n_so; q++) sels.id[sels.n++] = 1 + q;
     for (int a = 0; a < cfg.n_ap; a++) sels.id[sels.n++] = 1 + SOAP_MAX_SO + a;
     if (sels.n == 0) return 0;
+    {
+        const int per_shell = 2 * (cfg.dmo ? 1 : 4) * (full ? V_FULL : V_MIN);  // doubles of one shell: [bound][type][V]
+        const dim3 pg((unsigned)((per_shell + 127) / 128), n_list_host < 65535u ? n_list_host : 65535u);
+        LAUNCH(h, k_bank_prefix, pg, 128, 0, stream, ha, list, n_list_dev, per_shell);
+    }
     const dim3 grid(grid_for(n_list_host, 128), (unsigned)sels.n);
     if (full && !cfg.dmo) LAUNCH(h, (k_rows<V_FULL, 4>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);
     else if (full) LAUNCH(h, (k_rows<V_FULL, 1>), grid, 128, 0, stream, ha, cfg, list, n_list_dev, sels);

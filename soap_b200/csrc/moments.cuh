@@ -35,12 +35,13 @@ __device__ inline int find_cut(const Cuts& c, double r, int strict) {
     return -1;
 }
 
-// sum banks over shells [0, pos], bound states and types selected by masks
+// Sum of the banks of shells [0, pos] over the bound states and types selected by the masks.  The banks
+// handed to the row writer are CUMULATIVE over shells (k_bank_prefix), so shell `pos` holds that sum.
 template <int V>
 __device__ inline void sel_sum(const double* banks, int NTY, int pos, bool bound_only, unsigned typemask,
                                double* out) {
     for (int i = 0; i < V; i++) out[i] = 0.0;
-    for (int s = 0; s <= pos; s++)
+    for (int s = pos; s <= pos; s++)
         for (int b = bound_only ? 1 : 0; b < 2; b++)
             for (int t = 0; t < NTY; t++) {
                 int tcode = NTY == 1 ? 1 : t;

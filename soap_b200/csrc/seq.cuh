@@ -78,6 +78,13 @@ __device__ __forceinline__ bool quotient_greater(double c, double r, double bc, 
     return c / r > bc / br;
 }
 
+// running mass of the four half-mass groups (gas, dm, star, baryon = gas + star) : add a particle of type code tc
+__device__ __forceinline__ void group_add(double (&g)[4], uint32_t tc, double m) {
+    if (tc == 0u) { g[0] += m; g[3] += m; }
+    else if (tc == 1u) g[1] += m;
+    else if (tc == 2u) { g[2] += m; g[3] += m; }
+}
+
 __device__ __forceinline__ double hm_interp(double rmin_, double rmax_, double Wmin, double Wmax, double target) {
     // half_mass_radius.py:64-80
     if (Wmin == Wmax) return 0.5 * (rmin_ + rmax_);
@@ -157,11 +164,9 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
     int a_next = 0;                                // first aperture whose edge has not been passed
     double ap_thr[SOAP_MAX_APERTURES][4];
     {
-        double base[NCH];
+        double ga[4] = {0.0, 0.0, 0.0, 0.0}, gb[4] = {0.0, 0.0, 0.0, 0.0};  // group masses so far: all / bound
         uint32_t nbound = 0;
         double cum_all = 0.0, cum_b = 0.0, prev_r = 0.0, prev_cum = 0.0;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) base[ch] = 0.0;
         const bool do_so = n_so > 0;
         rs.finish();
         rs.start();
@@ -169,24 +174,20 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
             const Rec rc = rs.get(i);
             const double r = __longlong_as_double((long long)rc.rbits);
             const double m = (double)rc.m;
-            const int c = rec_class<NCH>(rc.flags);
             const uint32_t tc = NCH == 2 ? 1u : (rc.flags & 3u);
             const bool bound = (rc.flags & 4u) != 0;
-            // first record beyond each aperture radius: class sums in front of it (aperture_properties.py:310)
+            // first record beyond each aperture radius: group masses in front of it (aperture_properties.py:310)
             while (want_hmr && a_next < n_ap && r > cfg.ap_r[a_next]) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) ap_thr[a_next][g] = 0.5 * group_sum<NCH>(base, g, cfg.ap_incl[a_next] == 0);
+                for (int g = 0; g < 4; g++) ap_thr[a_next][g] = 0.5 * (cfg.ap_incl[a_next] == 0 ? gb[g] : ga[g]);
                 a_next++;
             }
             double w_ex[4];
-            if (want_hmr && bound && cfg.do_sub) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) w_ex[g] = group_sum<NCH>(base, g, true);
-            }
-            const double cb_ex_cls = bound_sum<NCH>(base);
-#pragma unroll
-            for (int ch = 0; ch < NCH; ch++)
-                if (c == ch) base[ch] += m;
+            for (int g = 0; g < 4; g++) w_ex[g] = gb[g];
+            const double cb_ex_cls = cum_b;
+            group_add(ga, tc, m);
+            if (bound) group_add(gb, tc, m);
             cum_all += m;  // np.cumsum order (SO_properties.py:400)
             if (do_so && i >= nskip_so && (n_searching > 0 || n_walking > 0 || !nn_found)) {
                 const float cm = so_cm32(cum_all, r, cfg.nu);
@@ -238,8 +239,8 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
             prev_r = r;
             prev_cum = cum_all;
             if (bound) {
-                const double cb_in_cls = bound_sum<NCH>(base);
                 cum_b += m;
+                const double cb_in_cls = cum_b;
                 if (cfg.do_sub) {
                     // Vmax of the bound subhalo (subhalo_properties.py:982-1045): first maximum of cum / r
                     if (nbound >= nskip_u && r > 0.0 && (!amU_ok || quotient_greater(cum_b, r, amU_c, amU_r))) {
@@ -259,7 +260,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
                         for (int g = 0; g < 4; g++)
                             if (in_group(g, tc)) {
                                 if (!(sub_hm_found & (2u << g)) && Mb_g[1 + g] != 0.0) {
-                                    const double w = group_sum<NCH>(base, g, true);
+                                    const double w = gb[g];
                                     if (w >= 0.5 * Mb_g[1 + g]) {
                                         sub_hm_found |= 2u << g;
                                         sub_hm[1 + g] = hm_interp(last_b[1 + g], r, w_ex[g], w, 0.5 * Mb_g[1 + g]);
@@ -276,7 +277,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         // apertures whose edge lies beyond the last record: totals inside
         while (want_hmr && a_next < n_ap) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) ap_thr[a_next][g] = 0.5 * group_sum<NCH>(base, g, cfg.ap_incl[a_next] == 0);
+            for (int g = 0; g < 4; g++) ap_thr[a_next][g] = 0.5 * (cfg.ap_incl[a_next] == 0 ? gb[g] : ga[g]);
             a_next++;
         }
     }
@@ -452,9 +453,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
             for (int a = 0; a < n_ap; a++)
                 for (int g = 0; g < 4; g++)
                     if (ap_thr[a][g] > 0.0) ap_want |= 1ull << (a * 4 + g);
-        double base[NCH];
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) base[ch] = 0.0;
+        double ga[4] = {0.0, 0.0, 0.0, 0.0}, gb[4] = {0.0, 0.0, 0.0, 0.0};  // group masses so far: all / bound
         double cum_all = 0.0, last_dm_r = 0.0;
         bool have_dm = false;
         double last_m[2][4];  // radius of the previous member of (all / bound-only, group)
@@ -483,20 +482,13 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
             const Rec rc = rs.get(i);
             const double r = __longlong_as_double((long long)rc.rbits);
             const double m = (double)rc.m;
-            const int c = rec_class<NCH>(rc.flags);
             const uint32_t tc = NCH == 2 ? 1u : (rc.flags & 3u);
             const bool bound = (rc.flags & 4u) != 0;
             double w_ex[2][4];
-            if (want_hmr && n_ap > 0) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    w_ex[0][g] = group_sum<NCH>(base, g, false);
-                    w_ex[1][g] = group_sum<NCH>(base, g, true);
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < NCH; ch++)
-                if (c == ch) base[ch] += m;
+            for (int g = 0; g < 4; g++) { w_ex[0][g] = ga[g]; w_ex[1][g] = gb[g]; }
+            group_add(ga, tc, m);
+            if (bound) group_add(gb, tc, m);
             cum_all += m;
             const double rs = fmax(cfg.soft[tc], r);
             if (n_ap > 0) {
@@ -541,7 +533,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
 #pragma unroll
                     for (int g = 0; g < 4; g++)
                         if (in_group(g, tc) && ap_thr[a][g] > 0.0 && !((ap_found >> (a * 4 + g)) & 1ull)) {
-                            const double w = group_sum<NCH>(base, g, excl);
+                            const double w = excl ? gb[g] : ga[g];
                             if (w >= ap_thr[a][g]) {
                                 ap_found |= 1ull << (a * 4 + g);
                                 sr->ap_hmr[a][g] = hm_interp(last_m[excl ? 1 : 0][g], r, w_ex[excl ? 1 : 0][g], w, ap_thr[a][g]);

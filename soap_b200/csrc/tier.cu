@@ -537,8 +537,9 @@ int launch_front(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const u
     unsigned int grid = (unsigned int)(h->sm_count * per_sm);
     const unsigned int need = (n_upper + NW - 1) / NW;
     if (grid > need) grid = need < 1 ? 1 : need;
-    LAUNCH(h, kern, grid, 32 * NW, smem, stream, c->v, ha, cfg, list, n_list, overflow, n_overflow, queue_cursor, try_list,
-           ctr, recs, pids, item_minr, item_minfof, bank_stride);
+    LAUNCH_N(h, CAP <= 256 ? "k_tier_front<256>" : "k_tier_front<1024>", kern, grid, 32 * NW, smem, stream, c->v, ha, cfg,
+             list, n_list, overflow, n_overflow, queue_cursor, try_list, ctr, recs, pids, item_minr, item_minfof,
+             bank_stride);
     return 0;
 }
 
@@ -562,7 +563,8 @@ int launch_tier_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     unsigned int grid = (unsigned int)(h->sm_count * per_sm);
     const unsigned int need = (n_upper + NW - 1) / NW;
     if (grid > need) grid = need < 1 ? 1 : need;
-    LAUNCH(h, kern, grid, 32 * NW, smem, stream, c->v, ha, cfg, list, n_list, pids, (int)slot, smem_banks);
+    LAUNCH_N(h, "k_tier_moments", kern, grid, 32 * NW, smem, stream, c->v, ha, cfg, list, n_list, pids, (int)slot,
+             smem_banks);
     return 0;
 }
 
