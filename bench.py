@@ -425,12 +425,37 @@ def main():
 
     t0 = time.time()
     hydro = args.workload.startswith("config3") or args.workload == "config4"
-    data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank + (1 if hydro else 0) + (1 if args.workload == "config4" else 0),
-                                  device=gen_dev, max_np=max_np, type_fractions=HYDRO_TYPES if hydro else None,
-                                  **({"m_part": M_PART[args.workload]} if args.workload in M_PART else {}))
+    # N > 1 (DMO recipe): ONE periodic volume of N times the single-GPU workload (weak scaling), cut into N Peano-Hilbert
+    # chunks that carry their own ghost shells (BASELINE config 5); rank r generates the particles of
+    # chunk r on its device from the shared halo catalogue -- the volume is never materialised as a whole.
+    volume = world > 1 and not hydro and args.impl == "ours"
+    n_halos_total = n_halos * world
+    if volume:
+        from soap_b200 import chunk_tasks as ct
+
+        Lv = L * world ** (1.0 / 3.0)
+        cat = synth.volume_catalogue(n_part * world, n_halos * world, Lv, seed=SEED, max_np=max_np)
+        H_all = {k: cat[k] for k in ("cofp", "index", "search_radius", "read_radius", "nr_bound_part", "is_central")}
+        hs, csz = ct.peano_decomposition(Lv, H_all, world)
+        mine = ct.chunk_halos(hs, csz, ct.assign_chunks(len(csz), world)[rank][0])
+        data, halos = synth.volume_chunk(cat, mine["index"], device=gen_dev)
+        n_own = int(sum(len(d["Masses"]) for d in data.values()))
+        wl_name = (f"{args.workload} x {world}: ONE synthetic DMO volume, L={Lv:.1f} Mpc, {n_part * world} particles, "
+                   f"{n_halos_total} halos, cut into {world} Peano-Hilbert chunks with ghost shells (slab cover of the read "
+                   f"spheres), one per GPU, particles generated per chunk on the device; SO 200_crit/200_mean/500_crit/BN98 "
+                   f"+ BoundSubhalo")
+        L = Lv
+        cp = synth.coordinate_unit_params(L)
+        n_part = n_own  # this rank's particles, ghost shell included
+        del cat, H_all, hs
+    else:
+        data, halos = synth.nfw_chunk(n_part, n_halos, L, seed=SEED + rank + (1 if hydro else 0) + (1 if args.workload == "config4" else 0),
+                                      device=gen_dev, max_np=max_np, type_fractions=HYDRO_TYPES if hydro else None,
+                                      **({"m_part": M_PART[args.workload]} if args.workload in M_PART else {}))
     if have_cuda:
         torch.cuda.synchronize()
-    log(f"[bench] rank {rank}: generated {args.workload} on {gen_dev} in {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: generated {args.workload} ({n_part} particles, {int(halos['cofp'].shape[0])} halos) on {gen_dev} "
+        f"in {time.time() - t0:.1f}s")
 
     # ------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -486,8 +511,13 @@ def main():
     # Results stay per rank ("each rank appends to its own ResultSet"); what NCCL moves is a float32
     # copy of the table (PropertyTable's output precision) gathered to rank 0 asynchronously, overlapped with the
     # next chunk's kernels and waited for before the timed region ends.
-    gather32 = [torch.empty((H, ncol), dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    send32 = torch.empty((H, ncol), dtype=torch.float32, device=dev) if world > 1 else None
+    Hmax = H
+    if world > 1:
+        hm = torch.tensor([H], dtype=torch.int64, device=dev)
+        dist.all_reduce(hm, op=dist.ReduceOp.MAX)
+        Hmax = int(hm.item())
+    gather32 = [torch.empty((Hmax, ncol), dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    send32 = torch.zeros((Hmax, ncol), dtype=torch.float32, device=dev) if world > 1 else None
     pending = []
 
     def step_device():
@@ -497,7 +527,7 @@ def main():
             for w in pending:
                 w.wait()
             pending.clear()
-            send32.copy_(table)
+            send32[:H].copy_(table)
             pending.append(dist.gather(send32, gather32, dst=0, async_op=True))
         return chunk, res
 
@@ -544,6 +574,11 @@ def main():
     status = res.status.cpu().numpy()
     n_ok = int((status == 0).sum())
     pairs = stats.get("pairs", 0.0)
+    pairs_all, n_ok_all, n_part_all = pairs, n_ok, n_part
+    if world > 1:
+        tot = torch.tensor([pairs, n_ok, n_part], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        pairs_all, n_ok_all, n_part_all = float(tot[0].item()), int(tot[1].item()), int(tot[2].item())
 
     # ----------------------------------------------------------------- e2e
     e2e = None
@@ -595,7 +630,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": H * world / dt, "unit": "halos/s", "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": n_halos_total / dt, "unit": "halos/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt,
                "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i", "numa_node": numa}
 
@@ -668,16 +703,16 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": "halos_per_s", "value": H * world / (ms_step * 1e-3), "unit": "halos/s",
+            "metric": "halos_per_s", "value": n_halos_total / (ms_step * 1e-3), "unit": "halos/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl_name, "l2": "inputs (48 B x particles) larger than L2; no flush needed",
-                       "halos_ok": n_ok, "halos": H, "internal_mesh_res": int(stats.get("res", 0)),
+                       "halos_ok": n_ok_all, "halos": n_halos_total, "particles_incl_ghosts": int(n_part_all), "internal_mesh_res": int(stats.get("res", 0)),
                        "ladder_rounds": int(stats.get("rounds", 0)), "ncol": ncol,
                        "parallelism": f"{world} chunks, one per GPU, no data-path collective; float32 result tables gathered to "
                                       "rank 0 over NCCL asynchronously (overlapped with the next chunk)"},
-            "pairs_per_s": pairs * world / (ms_step * 1e-3), "pairs_per_step": int(pairs),
+            "pairs_per_s": pairs_all / (ms_step * 1e-3), "pairs_per_step": int(pairs_all),
             "candidates_per_step": int(stats.get("candidates", 0)),
             "algorithmic_gbs_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_whole_step": round(total_alg / (ms_step * 1e-3) / 1e9 / peak, 4),

@@ -57,9 +57,35 @@ def hilbert_keys(ix, iy, iz, bits):
     return key
 
 
-def peano_decomposition(boxsize, halo, nr_chunks, bits_per_dimension=10):
-    """domain_decomposition.py:64-142 on one rank.  ``halo`` is the dict of halo
-    arrays (cofp [H,3], ...).  Returns (halo sorted along the curve, chunk_size)."""
+def peano_decomposition(boxsize, halo, nr_chunks, bits_per_dimension=10, separate_chunks=None):
+    """domain_decomposition.py:9-142 on one rank.  ``halo`` is the dict of halo
+    arrays (cofp [H,3], ...).  Returns (halo in chunk order, chunk_size).
+
+    ``separate_chunks`` (list of {"n_bound_threshold", "n_halo_per_chunk"}, sorted by descending threshold
+    like the parameter file's, :28-60,97-140) takes the halos with more bound particles than the smallest
+    threshold out of the curve and appends them, largest first, as extra chunks of at most
+    ``n_halo_per_chunk`` halos of the first threshold they exceed -- a 10^6-particle cluster with its 5 Mpc
+    ghost shell then does not share a GPU's memory with a thousand neighbours."""
+    if separate_chunks:
+        nb = np.asarray(halo["nr_bound_part"])
+        large = nb > separate_chunks[-1]["n_bound_threshold"]  # :38-39
+        if large.any():
+            small = {k: np.asarray(v)[~large] for k, v in halo.items()}
+            big = {k: np.asarray(v)[large] for k, v in halo.items()}
+            order = np.argsort(big["nr_bound_part"], kind="stable")[::-1]  # :100-102
+            big = {k: v[order] for k, v in big.items()}
+            sizes, i_thr, i_h, n_big = [], 0, 0, len(order)
+            while i_h < n_big:  # :105-117
+                while separate_chunks[i_thr]["n_bound_threshold"] > big["nr_bound_part"][i_h]:
+                    i_thr += 1
+                c = min(int(separate_chunks[i_thr]["n_halo_per_chunk"]), n_big - i_h)
+                sizes.append(c)
+                i_h += c
+            if len(small["index"]):
+                out, chunk_size = peano_decomposition(boxsize, small, nr_chunks, bits_per_dimension)
+                out = {k: np.concatenate([out[k], big[k]], axis=0) for k in out}  # :120-128
+                return out, np.concatenate([chunk_size, np.array(sizes, dtype=np.int64)])
+            return big, np.array(sizes, dtype=np.int64)
     centres = np.asarray(halo["cofp"], dtype=np.float64)
     nr_halos = centres.shape[0]
     nr_chunks = max(1, min(int(nr_chunks), nr_halos))  # :76-78
@@ -117,34 +143,72 @@ def ghost_mask(pos, cofp, read_radius, boxsize, cells_per_dim=64):
     return keep
 
 
+def slab_cover(cofp, read_radius, boxsize, cells_per_dim=64):
+    """Per dimension, which of the ``cells_per_dim`` slabs of the box are touched by some halo's
+    [c - r, c + r] (periodic): bool [3, cells_per_dim]."""
+    cofp = np.asarray(cofp, dtype=np.float64)
+    rr = np.asarray(read_radius, dtype=np.float64)
+    n = int(cells_per_dim)
+    cs = boxsize / n
+    out = np.ones((3, n), dtype=bool)
+    for d in range(3):
+        lo = np.floor((cofp[:, d] - rr) / cs).astype(np.int64)
+        hi = np.floor((cofp[:, d] + rr) / cs).astype(np.int64)
+        if np.any(hi - lo + 1 >= n):
+            continue
+        shift = (-lo.min() // n + 1) * n
+        lo, hi = lo + shift, hi + shift
+        diff = np.zeros(int(hi.max()) + 2, dtype=np.int64)
+        np.add.at(diff, lo, 1)
+        np.add.at(diff, hi + 1, -1)
+        slab = np.zeros(n, dtype=bool)
+        slab[np.nonzero(np.cumsum(diff)[:-1] > 0)[0] % n] = True
+        out[d] = slab
+    return out
+
+
+def ghost_mask_device(pos, cofp, read_radius, boxsize, cells_per_dim=64):
+    """``ghost_mask`` for positions that are already on the device (torch [N,3]): the slab cover is a few
+    hundred bytes computed on the host from the chunk's halos, the per-particle test runs where the
+    particles are.  Returns a bool tensor on pos.device."""
+    import torch
+
+    cover = torch.as_tensor(slab_cover(cofp, read_radius, boxsize, cells_per_dim), device=pos.device)
+    cs = boxsize / cells_per_dim
+    cell = torch.clamp(torch.floor(torch.remainder(pos, boxsize) / cs).to(torch.int64), 0, cells_per_dim - 1)
+    return cover[0][cell[:, 0]] & cover[1][cell[:, 1]] & cover[2][cell[:, 2]]
+
+
 def gather_tables(table, index, dst=0, group=None):
-    """Gather per-rank [H_r, ncol] tables (+ their halo indices) to rank dst.
-    Tables are torch tensors on the device the process group works on (CUDA for
-    NCCL, CPU for gloo).  Returns (table, index) concatenated on dst, else None."""
+    """Gather per-rank [H_r, ncol] tables (+ their halo indices) to rank dst in ONE collective: the index
+    travels as an extra float64 column (exact below 2^53).  Tables are torch tensors on the device the
+    process group works on (CUDA for NCCL, CPU for gloo); a rank that owns no chunk (more ranks than
+    chunks) takes part with an empty table of the common width.  Returns (table, index) on dst, else None."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return table, index
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=table.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    nmax, ncol = max(sizes), table.shape[1]
-    pad_t = torch.zeros((nmax, ncol), dtype=table.dtype, device=table.device)
-    pad_t[: table.shape[0]] = table
-    pad_i = torch.full((nmax,), -1, dtype=torch.int64, device=table.device)
-    pad_i[: index.shape[0]] = index
-    bufs_t = [torch.empty_like(pad_t) for _ in range(world)] if rank == dst else None
-    bufs_i = [torch.empty_like(pad_i) for _ in range(world)] if rank == dst else None
-    dist.gather(pad_t, bufs_t, dst=dst, group=group)
-    dist.gather(pad_i, bufs_i, dst=dst, group=group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    meta = torch.tensor([table.shape[0], table.shape[1] if table.ndim == 2 else 0], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    sizes = [int(m[0].item()) for m in metas]
+    ncol = max(int(m[1].item()) for m in metas)
+    nmax = max(sizes)
+    if nmax == 0:
+        return (torch.zeros((0, ncol), dtype=torch.float64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)) if rank == dst else None
+    pad = torch.zeros((nmax, ncol + 1), dtype=torch.float64, device=dev)
+    if table.shape[0]:
+        pad[: table.shape[0], :ncol] = table.to(dev)
+        pad[: index.shape[0], ncol] = index.to(dev).to(torch.float64)
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
     if rank != dst:
         return None
-    t = torch.cat([b[:s] for b, s in zip(bufs_t, sizes)])
-    i = torch.cat([b[:s] for b, s in zip(bufs_i, sizes)])
-    return t, i
+    t = torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+    return t[:, :ncol].contiguous(), t[:, ncol].to(torch.int64)
 
 
 # columns of the result table the re-read loop looks at (soap_result_layout: InputHalos/status,
@@ -154,7 +218,7 @@ STATUS_RADIUS_TOO_SMALL = 1
 
 
 def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, group=None, reread=False,
-               max_passes=20):
+               max_passes=20, separate_chunks=None):
     """Process every chunk owned by this rank with ``compute(chunk_data,
     chunk_halos) -> torch [H_c, ncol]`` and gather the rows on rank 0, ordered by
     halo index.  ``data[ptype]`` are numpy arrays of the whole box here (a real
@@ -168,7 +232,7 @@ def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, gr
     reached; everything else keeps its row from the pass that finished it."""
     import torch
 
-    halo_s, chunk_size = peano_decomposition(boxsize, halo, nr_chunks)
+    halo_s, chunk_size = peano_decomposition(boxsize, halo, nr_chunks, separate_chunks=separate_chunks)
     mine = assign_chunks(len(chunk_size), world_size)[rank]
     tables, indices = [], []
     for c in mine:
@@ -197,14 +261,23 @@ def run_chunks(data, halo, boxsize, nr_chunks, compute, rank=0, world_size=1, gr
             hc["search_radius"][sel[again]] = tn[again, COL_SEARCH_RADIUS]
             hc["read_radius"][sel[again]] = tn[again, COL_READ_RADIUS]
             sel = sel[again]
+        else:
+            # the reference repeats until no halo is left (chunk_tasks.py:188-367); give up loudly instead
+            raise RuntimeError(f"chunk {c}: {len(sel)} halos still ask for a larger read radius after {max_passes} passes")
         t = table_c
+        bad = (t[:, COL_STATUS] >= 2).cpu().numpy() if reread else np.zeros(0, dtype=bool)
+        if bad.any():
+            # count mismatch / SO not found within 20 Mpc / root bracket: RuntimeErrors in the reference
+            # (subhalo_properties.py:2642-2646, SO_properties.py:150-153,208)
+            i = int(np.flatnonzero(bad)[0])
+            raise RuntimeError(f"chunk {c}: halo index={int(np.asarray(hc['index'])[i])} failed with status "
+                               f"{int(t[i, COL_STATUS].item())} ({int(bad.sum())} halos in this chunk)")
         tables.append(t)
         indices.append(torch.as_tensor(np.asarray(hc["index"], dtype=np.int64), device=t.device))
     if tables:
         table, index = torch.cat(tables), torch.cat(indices)
-    else:
-        dev = "cpu" if group is None or not torch.cuda.is_available() else torch.device("cuda", torch.cuda.current_device())
-        table, index = torch.zeros((0, 0), dtype=torch.float64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)
+    else:  # more ranks than chunks: this rank has nothing; gather_tables gives the table its width
+        table, index = torch.zeros((0, 0), dtype=torch.float64), torch.zeros(0, dtype=torch.int64)
     got = gather_tables(table, index, 0, group)
     if got is None:
         return None

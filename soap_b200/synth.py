@@ -360,3 +360,175 @@ def to_numpy(data, halos):
     d = {t: {k: v.cpu().numpy() for k, v in dd.items()} for t, dd in data.items()}
     h = {k: v.cpu().numpy() for k, v in halos.items()}
     return d, h
+
+
+# ------------------------------------------------------------ one volume, many chunks
+# BASELINE config 5 (and the N > 1 runs of bench.py): ONE periodic volume of the config-2 recipe whose
+# particles are never materialised as a whole.  A global halo catalogue is drawn once (numpy, a few bytes per
+# halo); the particles of a chunk -- the members of every halo that reaches into the chunk's region, ghost shell
+# included, plus the background of the region's cells -- are generated where they are needed, on the device,
+# from a counter-based hash of (global particle id, stream): a particle that lies in the ghost shells of two
+# chunks comes out bit-identical in both, like a particle read twice from the same snapshot.
+
+_M64 = (1 << 64) - 1
+
+
+def _i64(x):
+    """python int (mod 2^64) -> the int64 with the same bits"""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _mix64(x):
+    """splitmix64 finaliser on an int64 tensor (wrapping arithmetic, logical shifts emulated)"""
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * _i64(0xBF58476D1CE4E5B9)
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * _i64(0x94D049BB133111EB)
+    return x ^ ((x >> 31) & ((1 << 33) - 1))
+
+
+def hash_uniform(ids, stream, seed):
+    """uniform float64 in [0, 1) from (id, stream, seed); ids int64 tensor"""
+    import torch
+
+    x = _mix64(ids * _i64(0x9E3779B97F4A7C15) + _i64((stream + 1) * 0xD1B54A32D192ED03 + seed * 0x2545F4914F6CDD1D))
+    return ((x >> 11) & ((1 << 53) - 1)).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def volume_catalogue(n_part, n_halos, boxsize, seed=20261018, m_part=0.0843, min_np=20, max_np=2.0e6, slope=-1.9,
+                     halo_fraction=0.85, outer_factor=2.5, frac_central=0.95, bg_cells=64, a=SCALE_FACTOR):
+    """The global halo catalogue of a volume (numpy): bound / outskirt particle numbers, concentration, R_200c,
+    centres, first global particle id of every halo, and the background particle count of every cell of a
+    bg_cells^3 grid.  Same distributions as nfw_chunk."""
+    rng = np.random.default_rng(seed)
+    rho200 = 200.0 * CRITICAL_DENSITY * a**3
+    e = slope + 1.0
+    nh = np.floor((min_np**e + rng.random(n_halos) * (max_np**e - min_np**e)) ** (1.0 / e)).astype(np.int64)
+    nh = np.sort(np.maximum(nh, min_np))[::-1].copy()
+
+    def outskirts(nh):
+        conc = 7.0 * (nh / 100.0) ** (-0.1)
+        mu_c = np.log1p(conc) - conc / (1.0 + conc)
+        xo = outer_factor * conc
+        mu_o = np.log1p(xo) - xo / (1.0 + xo)
+        return conc, mu_c, mu_o, np.floor((mu_o / mu_c - 1.0) * nh).astype(np.int64)
+
+    conc, mu_c, mu_o, n_out = outskirts(nh)
+    budget = int(halo_fraction * n_part)
+    while int((nh + n_out).sum()) > budget:  # shave the most massive halos until the budget fits
+        k = int(np.argmax(np.cumsum((nh + n_out)[::-1])[::-1] <= budget)) or 1
+        nh[:k] = np.maximum(nh[:k] // 2, min_np)
+        conc, mu_c, mu_o, n_out = outskirts(nh)
+    tot = nh + n_out
+    start = np.cumsum(tot) - tot
+    n_in_halos = int(tot.sum())
+    n_bg = n_part - n_in_halos
+    ncell = bg_cells**3
+    bg_count = np.full(ncell, n_bg // ncell, dtype=np.int64)
+    bg_count[: n_bg % ncell] += 1
+    r200 = (nh * m_part / (rho200 * 4.0 / 3.0 * math.pi)) ** (1.0 / 3.0)
+    is_central = (rng.random(n_halos) < frac_central).astype(np.int32)
+    return dict(nh=nh, n_out=n_out, tot=tot, start=start, conc=conc, mu_c=mu_c, mu_o=mu_o, r200=r200,
+                cofp=boxsize * rng.random((n_halos, 3)), is_central=is_central, n_in_halos=n_in_halos,
+                bg_count=bg_count, bg_start=n_in_halos + np.cumsum(bg_count) - bg_count, bg_cells=bg_cells,
+                boxsize=float(boxsize), m_part=float(m_part), seed=int(seed), outer_factor=float(outer_factor),
+                index=np.arange(n_halos, dtype=np.int64), nr_bound_part=nh.copy(),
+                # nothing of a halo lies beyond outer_factor R_200c: upper bounds for the decomposition's ghost shells
+                search_radius=np.maximum(1.01 * r200, 1.0e-3), read_radius=np.maximum(1.01 * r200, 5.0))
+
+
+def volume_chunk(cat, halo_sel, device="cpu", cells_per_dim=64, sort_cells=32):
+    """Particles and halo arrays of one chunk of the volume: ``halo_sel`` = catalogue rows of the chunk's halos.
+    Returns (data, halos) like nfw_chunk (torch tensors on ``device``), the particles being every particle of the
+    volume that lies in the chunk's slab cover (chunk_tasks.slab_cover of the chunk's read spheres)."""
+    import torch
+
+    from .chunk_tasks import slab_cover
+
+    L, seed = cat["boxsize"], cat["seed"]
+    halo_sel = np.asarray(halo_sel)
+    cover = slab_cover(cat["cofp"][halo_sel], cat["read_radius"][halo_sel], L, cells_per_dim)
+    cs = L / cells_per_dim
+    # halos that reach into the covered region: some covered slab within [c - R, c + R] in every dimension
+    R = cat["outer_factor"] * cat["r200"]
+    touch = np.ones(len(R), dtype=bool)
+    for d in range(3):
+        if cover[d].all():
+            continue
+        csum = np.concatenate([[0], np.cumsum(np.tile(cover[d], 3))])  # three periods: ranges may wrap
+        lo = np.floor((cat["cofp"][:, d] - R) / cs).astype(np.int64) + cells_per_dim
+        hi = np.floor((cat["cofp"][:, d] + R) / cs).astype(np.int64) + cells_per_dim
+        touch &= (csum[np.minimum(hi + 1, 3 * cells_per_dim)] - csum[np.maximum(lo, 0)]) > 0
+    hs = np.flatnonzero(touch)
+    t = lambda x, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(x), device=device).to(dt)  # noqa: E731
+    tot = t(cat["tot"][hs], torch.int64)
+    n = int(tot.sum().item())
+    hid = torch.repeat_interleave(torch.arange(len(hs), device=device), tot)
+    local = torch.arange(n, device=device) - (torch.cumsum(tot, 0) - tot)[hid]
+    gid = t(cat["start"][hs], torch.int64)[hid] + local  # global particle id
+    nh, conc, mu_c, mu_o, r200 = (t(cat[k][hs]) for k in ("nh", "conc", "mu_c", "mu_o", "r200"))
+    bound = local < nh[hid].to(torch.int64)
+    xmax = float(cat["outer_factor"] * cat["conc"].max()) * 1.001
+    xt = torch.logspace(-5, math.log10(xmax), 8192, dtype=torch.float64, device=device)
+    mt = torch.log1p(xt) - xt / (1.0 + xt)
+    uu = hash_uniform(gid, 0, seed)
+    mu_lo = torch.where(bound, torch.zeros_like(uu), mu_c[hid])
+    mu_hi = torch.where(bound, mu_c[hid], mu_o[hid])
+    m = mu_lo + uu * (mu_hi - mu_lo)
+    j = torch.clamp(torch.searchsorted(mt, m), 1, mt.numel() - 1)
+    x = xt[j - 1] + (m - mt[j - 1]) / (mt[j] - mt[j - 1]) * (xt[j] - xt[j - 1])
+    x = torch.where(bound, torch.minimum(x, conc[hid] * (1.0 - 1e-9)), x)
+    r = r200[hid] * x / conc[hid]
+    r = torch.where(local == 0, torch.zeros_like(r), r)
+    del uu, mu_lo, mu_hi, m, j, x
+    phi = 2.0 * math.pi * hash_uniform(gid, 1, seed)
+    st = 2.0 * hash_uniform(gid, 2, seed) - 1.0
+    ct_ = torch.sqrt((1.0 - st) * (1.0 + st))
+    pos = torch.stack([r * torch.cos(phi) * st, r * torch.sin(phi) * st, r * ct_], dim=1) + t(cat["cofp"][hs])[hid]
+    pos = torch.remainder(pos, L)
+    del phi, st, ct_
+    ghid = t(cat["index"][hs], torch.int64)[hid]
+    # bound radius of every halo -> search radius, before the cut (a halo of the chunk is complete by construction)
+    rb = torch.zeros(len(hs), dtype=torch.float64, device=device)
+    rb.scatter_reduce_(0, hid[bound], r[bound], reduce="amax", include_self=True)
+    # keep what lies in the region
+    cov = torch.as_tensor(cover, device=device)
+    cell = torch.clamp(torch.floor(pos / cs).to(torch.int64), 0, cells_per_dim - 1)
+    keep = cov[0][cell[:, 0]] & cov[1][cell[:, 1]] & cov[2][cell[:, 2]]
+    pos, gid_k = pos[keep], gid[keep]
+    grnr = torch.where(bound, ghid, torch.full_like(ghid, -1))[keep].to(torch.int32)
+    fof = ghid[keep].to(torch.int32)
+    del cell, keep, hid, local, bound, r, ghid, gid
+    # background of the covered cells
+    idx = np.flatnonzero((cover[0][:, None, None] & cover[1][None, :, None] & cover[2][None, None, :]).ravel())
+    assert cat["bg_cells"] == cells_per_dim
+    cnt = t(cat["bg_count"][idx], torch.int64)
+    nb = int(cnt.sum().item())
+    cid = torch.repeat_interleave(torch.arange(len(idx), device=device), cnt)
+    bgid = t(cat["bg_start"][idx], torch.int64)[cid] + (torch.arange(nb, device=device) - (torch.cumsum(cnt, 0) - cnt)[cid])
+    cflat = t(idx, torch.int64)[cid]
+    org = torch.stack([cflat // (cells_per_dim * cells_per_dim), (cflat // cells_per_dim) % cells_per_dim,
+                       cflat % cells_per_dim], dim=1).to(torch.float64) * cs
+    bpos = org + cs * torch.stack([hash_uniform(bgid, s, seed) for s in (0, 1, 2)], dim=1)
+    pos = torch.cat([pos, torch.clamp(bpos, max=L * (1.0 - 1e-16))])
+    gid_all = torch.cat([gid_k, bgid])
+    grnr = torch.cat([grnr, torch.full((nb,), -1, dtype=torch.int32, device=device)])
+    fof = torch.cat([fof, torch.full((nb,), -1, dtype=torch.int32, device=device)])
+    del org, bpos, cid, cflat, bgid, gid_k
+    vel = (1000.0 * (torch.stack([hash_uniform(gid_all, s, seed) for s in (3, 4, 5)], dim=1) - 0.5)).to(torch.float32)
+    npart = pos.shape[0]
+    # SWIFT-like coarse cell order, hashed within a cell
+    ci = torch.clamp((pos / (L / sort_cells)).floor().to(torch.int64), 0, sort_cells - 1)
+    key = ((ci[:, 0] * sort_cells + ci[:, 1]) * sort_cells + ci[:, 2]) * (1 << 20) + (_mix64(gid_all) & ((1 << 20) - 1))
+    order = torch.argsort(key)
+    del key, ci, gid_all
+    data = {1: dict(Coordinates=pos[order].contiguous(), Masses=torch.full((npart,), cat["m_part"], dtype=torch.float32, device=device),
+                    Velocities=vel[order].contiguous(), GroupNr_bound=grnr[order].contiguous(), FOFGroupIDs=fof[order].contiguous())}
+    # halo arrays of the chunk
+    pos_of = {int(h): i for i, h in enumerate(hs)}
+    rows = np.array([pos_of[int(h)] for h in halo_sel], dtype=np.int64)
+    rb_c = rb[torch.as_tensor(rows, device=device)]
+    sr = torch.clamp(1.01 * rb_c, min=1.0e-3)
+    halos = dict(cofp=t(cat["cofp"][halo_sel]), search_radius=sr, read_radius=torch.clamp(sr, min=5.0),
+                 is_central=t(cat["is_central"][halo_sel], torch.int32), nr_bound_part=t(cat["nh"][halo_sel], torch.int64),
+                 index=t(cat["index"][halo_sel], torch.int64))
+    return data, halos

@@ -114,12 +114,60 @@ def test_reread_loop_repeats_only_the_halos_whose_region_was_too_small():
     assert (t0.numpy()[:, 0] == 1).sum() == (need > 3.0).sum()
 
 
-def _worker(rank, world, port, q):
+def test_separate_chunks_isolate_the_largest_halos():
+    """domain_decomposition.py:28-60,97-140: halos above the smallest threshold leave the curve and come last,
+    largest first, in chunks of n_halo_per_chunk of the first threshold they exceed"""
+    data, halo = _box()
+    rng = np.random.default_rng(1)
+    halo["nr_bound_part"] = rng.integers(20, 1000, size=60)
+    halo["nr_bound_part"][[4, 17, 33, 50, 51]] = [90000, 2000000, 15000, 700000, 12000]
+    sep = [{"n_bound_threshold": 500000, "n_halo_per_chunk": 1}, {"n_bound_threshold": 10000, "n_halo_per_chunk": 2}]
+    hs, cs = ct.peano_decomposition(L, halo, 5, separate_chunks=sep)
+    assert cs.tolist() == [11, 11, 11, 11, 11, 1, 1, 2, 1] and cs.sum() == 60
+    assert hs["nr_bound_part"][55:].tolist() == [2000000, 700000, 90000, 15000, 12000]
+    assert sorted(hs["index"].tolist()) == sorted(halo["index"].tolist())
+    # the isolated chunks still give the whole-box answer
+    t, i = ct.run_chunks(data, halo, L, 5, _compute, separate_chunks=sep)
+    order = np.argsort(halo["index"])
+    assert np.array_equal(t.numpy(), _whole_box(data, halo)[order])
+
+
+def test_device_ghost_cut_equals_host_ghost_cut():
+    data, halo = _box()
+    hs, cs = ct.peano_decomposition(L, halo, 6)
+    for c in range(6):
+        hc = ct.chunk_halos(hs, cs, c)
+        ref = ct.ghost_mask(data[1]["Coordinates"], hc["cofp"], hc["read_radius"], L)
+        got = ct.ghost_mask_device(torch.as_tensor(data[1]["Coordinates"]), hc["cofp"], hc["read_radius"], L)
+        assert np.array_equal(got.numpy(), ref) and 0 < ref.sum() < len(ref)
+
+
+def test_stragglers_and_fatal_rows_are_not_passed_through_silently():
+    data, halo = _box(nh=8)
+
+    def never(cd, hc):  # every halo keeps asking for a larger region
+        out = np.zeros((len(hc["index"]), 8))
+        out[:, 0], out[:, 4], out[:, 5] = 1, hc["search_radius"], 1.5 * hc["read_radius"]
+        return torch.as_tensor(out)
+
+    with pytest.raises(RuntimeError, match="still ask for a larger read radius"):
+        ct.run_chunks(data, halo, L, 2, never, reread=True, max_passes=3)
+
+    def fatal(cd, hc):  # status 2: Ntot > nr_bound_part is a RuntimeError in the reference
+        out = np.zeros((len(hc["index"]), 8))
+        out[0, 0] = 2
+        return torch.as_tensor(out)
+
+    with pytest.raises(RuntimeError, match="failed with status 2"):
+        ct.run_chunks(data, halo, L, 2, fatal, reread=True)
+
+
+def _worker(rank, world, port, q, nr_chunks=7):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         data, halo = _box()
-        got = ct.run_chunks(data, halo, L, 7, _compute, rank=rank, world_size=world)
+        got = ct.run_chunks(data, halo, L, nr_chunks, _compute, rank=rank, world_size=world)
         if rank == 0:
             q.put((got[0].numpy(), got[1].numpy()))
         else:
@@ -129,13 +177,14 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_ranks_gloo_gather_equals_whole_box():
+@pytest.mark.parametrize("world,nr_chunks", [(2, 7), (3, 2)])  # (3, 2): a rank that owns no chunk takes part in the gather
+def test_ranks_gloo_gather_equals_whole_box(world, nr_chunks):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, nr_chunks)) for r in range(world)]
     for p in procs:
         p.start()
     t, i = q.get(timeout=120)
