@@ -30,7 +30,7 @@ int soap_launch_rows(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, con
 int soap_launch_solve_seq(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
                           const unsigned int* n_list_dev, unsigned int n_list_host, const Rec* recs, uint32_t* next,
                           unsigned int* n_next, Counters* ctr, const unsigned long long* item_minr, const int32_t* item_minfof,
-                          cudaStream_t stream);
+                          int multi, cudaStream_t stream);
 int soap_write_input_cols(soap_handle* h, const HaloArrays& ha, int64_t nh, cudaStream_t stream);
 int soap_launch_kappa(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const Item* items,
                       const unsigned int* n_items_dev, unsigned int n_items_host, const uint32_t* acc_list,
@@ -1182,7 +1182,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             log.end(stream);
             log.begin("scan_solve", stream);
             if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr, item_minfof,
-                                      stream))
+                                      0, stream))
                 return -1;
             if (hc.n_try > 0) {
                 unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);

@@ -91,11 +91,17 @@ __device__ __forceinline__ double hm_interp(double rmin_, double rmax_, double W
     return rmin_ + (target - Wmin) / (Wmax - Wmin) * (rmax_ - rmin_);
 }
 
+// One attempt at the rung whose sphere is the first n records.  iter > 0: a further rung tried within the same
+// call (solve_seq_halo): results of the selections committed by the earlier attempts are kept and the commit range
+// reported to the moment stage starts at c_lo_first.  defer: on "needs a larger radius" do the ladder step but leave
+// the decision where the halo goes to the caller (*pending_out, *required_out).
 template <int NCH>
-__device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const uint32_t h, const uint32_t n,
+__device__ void solve_seq_once(const HaloArrays& ha, const DevCfg& cfg, const uint32_t h, const uint32_t n,
                                const Rec* __restrict__ R, uint32_t* __restrict__ next, unsigned int* __restrict__ n_next, Counters* ctr,
                                const unsigned long long* __restrict__ minr, const int32_t* __restrict__ minfof,
-                               const uint32_t n_min, Cuts* __restrict__ cuts_out, uint4* __restrict__ slots) {
+                               const uint32_t n_min, Cuts* __restrict__ cuts_out, uint4* __restrict__ slots, const int iter,
+                               const int c_lo_first, const bool defer, int* fail_out, bool* pending_out,
+                               double* required_out) {
     ScanRes* sr = ha.sres + h;
     RecStream rs;
     rs.R = R; rs.n = n; rs.s = slots;
@@ -338,7 +344,10 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
     const int p0 = ha.ndone[h];
     int p = p0;
     double so_r_[SOAP_MAX_SO];
-    for (int q = 0; q < SOAP_MAX_SO; q++) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; so_r_[q] = 0.0; }
+    for (int q = 0; q < SOAP_MAX_SO; q++) {
+        if (iter == 0) { sr->so_r[q] = 0.0; sr->so_mass[q] = 0.0; sr->so_exists[q] = 0; }
+        so_r_[q] = 0.0;
+    }
     // BoundSubhalo's particle counts and enclosing radius: of this rung if it is committed now, else as stored
     uint32_t bc[4];
     double enclose = 0.0;
@@ -385,9 +394,10 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         if (!fail) p++;
     }
     const int c_lo = p0, c_hi = p;
-    sr->ap_on = ap_on;
-    sr->pj_on = pj_on;
-    ha.commit_lo[h] = c_lo;
+    const int c_lo_u = iter ? c_lo_first : c_lo;  // first property committed by this call
+    sr->ap_on = (iter ? sr->ap_on : 0u) | ap_on;
+    sr->pj_on = (iter ? sr->pj_on : 0u) | pj_on;
+    ha.commit_lo[h] = c_lo_u;
     ha.commit_hi[h] = c_hi;
     ha.ndone[h] = p;
     if (p > p0 && fail < 2) atomicAdd(&ctr->mom_pairs, (unsigned long long)n);
@@ -396,7 +406,9 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         ha.status[h] = status;
         ha.state[h] = ST_DONE_FAIL;
     } else if (fail == 1) {
-        if (ladder_step(ha, h, required) && next) next[atomicAdd(n_next, 1u)] = h;
+        const bool pending = ladder_step(ha, h, required);
+        if (pending && !defer && next) next[atomicAdd(n_next, 1u)] = h;
+        *pending_out = pending;
     } else {
         ha.state[h] = ST_FINAL;
         atomicAdd(&ctr->pairs, (unsigned long long)n);
@@ -432,9 +444,11 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         // so one running maximum serves them all and is snapshotted when the walk passes each radius
         int qs[SOAP_MAX_SO], nq = 0;
         for (int q = 0; q < n_so; q++) {
-            sr->so_dm_missed[q] = 0.0;
-            sr->so_vmax_r[q] = 0.0;
-            sr->so_vmax_v[q] = 0.0;
+            if (iter == 0) {
+                sr->so_dm_missed[q] = 0.0;
+                sr->so_vmax_r[q] = 0.0;
+                sr->so_vmax_v[q] = 0.0;
+            }
             if (so_r_[q] > 0.0) {
                 int k = nq++;
                 while (k > 0 && so_r_[qs[k - 1]] > so_r_[q]) { qs[k] = qs[k - 1]; k--; }
@@ -445,7 +459,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         double bound_v = nq > 0 ? so_r_[qs[0]] : 0.0, bound_dm = bound_v;  // radius of the next variation to close
         double best_c = 0.0, best_r = 0.0;
         bool best_ok = false;
-        if (want_hmr)
+        if (want_hmr && iter == 0)
             for (int a = 0; a < n_ap; a++)
                 for (int g = 0; g < 4; g++) sr->ap_hmr[a][g] = 0.0;
         unsigned long long ap_found = 0ull, ap_want = 0ull;  // bit a * 4 + g
@@ -556,8 +570,66 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         }
     }
     rs.finish();
-    // shell cuts of the moment stage for the selections committed now
-    if (cuts_out && c_hi > c_lo && fail < 2) build_cuts(cuts_out[h], cfg, sr, c_lo, c_hi, n_so);
+    // shell cuts of the moment stage for the selections committed by this call
+    if (cuts_out && c_hi > c_lo_u && fail < 2) build_cuts(cuts_out[h], cfg, sr, c_lo_u, c_hi, n_so);
+    *fail_out = fail;
+    *required_out = required;
+}
+
+// The solve of one halo.  multi: the records at hand are those of the sphere of the furthest of ha.look[h] ladder
+// rungs, sorted by radius, each carrying in flags bits 4-7 the first rung whose periodic r2 test includes it
+// (tier.cu); ha.rung_cnt / ha.rung_msum hold the cumulative count and mass of every rung.  When the attempt at a
+// rung ends with "needs a larger radius" (an SO that no particle of the sphere reaches, halo_tasks.py:125-140) the
+// next rungs are tried right here on longer prefixes of the same records -- density gate, n_loop and ladder exactly as
+// if the halo had come back in a new round (halo_tasks.py:73-103,166-187) -- instead of costing a kernel sequence
+// each.  Only offered for configurations in which no selection depends on the sphere it was computed in.
+template <int NCH>
+__device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const uint32_t h, uint32_t n,
+                               const Rec* __restrict__ R, uint32_t* __restrict__ next, unsigned int* __restrict__ n_next, Counters* ctr,
+                               const unsigned long long* __restrict__ minr, const int32_t* __restrict__ minfof,
+                               const uint32_t n_min, Cuts* __restrict__ cuts_out, uint4* __restrict__ slots, const bool multi) {
+    const int look = multi ? ha.look[h] : 1;
+    const uint32_t n_all = multi ? ha.rung_cnt[(size_t)h * LOOK_MAX + (look - 1)] : n;
+    const int c_lo_first = ha.ndone[h];
+    const bool has_target = ha.central[h] == 1 && cfg.target_density > 0.0;  // halo_tasks.py:381
+    int j = 0;
+    for (int iter = 0;; iter++) {
+        int fail = 0;
+        bool pending = false;
+        double required = 0.0;
+        solve_seq_once<NCH>(ha, cfg, h, n, R, next, n_next, ctr, minr, minfof, n_min, cuts_out, slots, iter, c_lo_first,
+                            j + 1 < look, &fail, &pending, &required);
+        if (fail != 1 || !pending) return;
+        if (!(j + 1 < look)) return;  // not deferred: the halo is already on the next list
+        bool served = false;
+        while (j + 1 < look && required == 0.0) {
+            j++;
+            const uint32_t nj = ha.rung_cnt[(size_t)h * LOOK_MAX + j];
+            // the radial order must agree with the rung binning at the prefix boundary (the two come from
+            // different roundings of the same distance)
+            const bool ok = (nj == 0 || (int)((ld_rec(R + nj - 1).flags >> 4) & 15u) <= j) &&
+                            (nj >= n_all || (int)((ld_rec(R + nj).flags >> 4) & 15u) > j);
+            if (!ok) break;
+            ha.nloop[h] += 1;  // halo_tasks.py:75
+            const double r = ha.cur_r[h];
+            const double mj = ha.rung_msum[(size_t)h * LOOK_MAX + j];
+            const double density = mj / (4.0 / 3.0 * SOAP_PI * (r * r * r));
+            if (!has_target || density <= cfg.target_density) {
+                ha.cnt[h] = nj;
+                ha.msum[h] = mj;
+                ha.rung_r[h] = r;
+                ha.state[h] = ST_TRY;
+                n = nj;
+                served = true;
+                break;
+            }
+            if (!ladder_step(ha, h, 0.0)) return;  // out of read radius: status set
+        }
+        if (!served) {
+            if (next) next[atomicAdd(n_next, 1u)] = h;
+            return;
+        }
+    }
 }
 
 #endif  // __CUDACC__

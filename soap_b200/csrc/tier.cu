@@ -24,7 +24,7 @@ int soap_launch_rows(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, con
 int soap_launch_solve_seq(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
                           const unsigned int* n_list_dev, unsigned int n_list_host, const Rec* recs, uint32_t* next,
                           unsigned int* n_next, Counters* ctr, const unsigned long long* item_minr, const int32_t* item_minfof,
-                          cudaStream_t stream);
+                          int multi, cudaStream_t stream);
 int soap_launch_kappa_finish(soap_handle* h, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
                              const unsigned int* n_list_dev, unsigned int n_list_host, cudaStream_t stream);
 
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                                                         uint32_t* __restrict__ try_list, Counters* ctr,
                                                         Rec* __restrict__ recs, uint32_t* __restrict__ pids,
                                                         unsigned long long* __restrict__ item_minr,
-                                                        int32_t* __restrict__ item_minfof, int bank_stride) {
+                                                        int32_t* __restrict__ item_minfof, int bank_stride, int multi) {
     constexpr uint32_t CAND_MAX = 16u * CAP;  // larger sweeps belong to the CTA-wide kernels of the general path
     constexpr int U = 4;                      // candidate groups in flight per warp (memory-level parallelism)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
         const int64_t hidx = ha.index[h];
         const bool central = ha.central[h] == 1;
         double cur = ha.cur_r[h], r2max = 0.0;
-        int nloop = ha.nloop[h], nrows = 0, action = ACT_RETRY;
-        uint32_t n = 0, total = 0;
+        int nloop = ha.nloop[h], nrows = 0, action = ACT_RETRY, n_rungs = 1;
+        uint32_t n = 0, total = 0, n_gather = 0;
+        double r2rung[4] = {-1.0, -1.0, -1.0, -1.0};  // squared radii of the gathered rungs, accepted rung first
         bool look1 = false;  // the look-ahead sphere did not fit: sweep the current rung alone
         // ---------------------------------------------------------------- ladder rungs
         while (action == ACT_RETRY) {
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
             // density gate and ladder steps (halo_tasks.py:73-103,166-187)
             uint32_t ccum = 0;
             int kacc = 0;
+            n_rungs = 1;
             if (lane == 0) {
                 const bool has_target = central && cfg.target_density > 0.0;  // halo_tasks.py:381
                 double mcum = 0.0;
@@ -192,6 +194,28 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                             ha.rung_r[h] = r;
                             ha.commit_lo[h] = ha.commit_hi[h] = ha.ndone[h];
                             ha.state[h] = ST_TRY;
+                            // the rungs beyond the accepted one that this sweep covered travel with the records, so
+                            // that a solve which needs a larger radius can try them at once (seq.cuh)
+                            uint32_t call = ccum;
+                            double mall = mcum;
+                            ha.rung_cnt[(size_t)h * LOOK_MAX] = call;
+                            ha.rung_msum[(size_t)h * LOOK_MAX] = mall;
+                            int nrg = 1;
+                            if (multi) {
+                                uint32_t nall = ccum;
+                                for (int kk = k + 1; kk < nr; kk++) nall += cnt[kk];
+                                if (nall <= (uint32_t)CAP)
+                                    for (int kk = k + 1; kk < nr; kk++) {
+                                        call += cnt[kk];
+                                        mall += msum[kk];
+                                        ha.rung_cnt[(size_t)h * LOOK_MAX + nrg] = call;
+                                        ha.rung_msum[(size_t)h * LOOK_MAX + nrg] = mall;
+                                        nrg++;
+                                    }
+                            }
+                            ha.look[h] = nrg;
+                            n_rungs = nrg;
+                            n_gather = call;
                         }
                         break;
                     }
@@ -203,11 +227,20 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
             }
             action = __shfl_sync(0xffffffffu, action, 0);
             nloop = __shfl_sync(0xffffffffu, nloop, 0);
-            n = __shfl_sync(0xffffffffu, ccum, 0);
+            n_rungs = __shfl_sync(0xffffffffu, n_rungs, 0);
+            n = __shfl_sync(0xffffffffu, n_gather, 0);
             kacc = __shfl_sync(0xffffffffu, kacc, 0);
             if (action == ACT_TRY) {
-                cur = rr[kacc];
-                r2max = r2k[kacc];
+                // radius of the sphere that is gathered, squared radii of its rungs (accepted rung first)
+#pragma unroll
+                for (int k = 0; k < LOOK; k++) {
+                    r2rung[k] = -1.0;
+#pragma unroll
+                    for (int kk = 0; kk < LOOK; kk++) {
+                        if (kk == kacc + k) r2rung[k] = r2k[kk];
+                        if (kk == kacc + n_rungs - 1) { cur = rr[kk]; r2max = r2k[kk]; }
+                    }
+                }
             } else if (action == ACT_RETRY) {
                 cur = __shfl_sync(0xffffffffu, lane == 0 ? ha.cur_r[h] : 0.0, 0);
             }
@@ -240,7 +273,8 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
             for (int u = 0; u < U; u++) {
                 if (j0 + 32 * u >= total) break;  // warp-uniform
                 const uint32_t t = T[u];
-                const bool isin = in[u] && periodic_r2(X[u], Y[u], Z[u], cx, cy, cz, L, halfL) <= r2max;
+                const double r2 = periodic_r2(X[u], Y[u], Z[u], cx, cy, cz, L, halfL);
+                const bool isin = in[u] && r2 <= r2max;
                 const unsigned bal = __ballot_sync(0xffffffffu, isin);
                 const unsigned base = W.n_stage;
                 __syncwarp();
@@ -251,7 +285,11 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                     rc.rbits = rel_radius_bits(X[u], Y[u], Z[u], cx, cy, cz, L, halfL);
                     rc.m = v.mass[t];
                     const uint32_t tc = NCH == 2 ? 1u : (uint32_t)v.type[t];
-                    rc.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u);
+                    // first gathered rung whose periodic r2 test includes the particle (0 = the accepted rung)
+                    uint32_t rung = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) rung += (k + 1 < n_rungs && !(r2 <= r2rung[k])) ? 1u : 0u;
+                    rc.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u) | (rung << 4);
                     W.rec[slot] = rc;
                     W.pid[slot] = t;
                     const int32_t f = (int32_t)v.fof[t];
@@ -526,7 +564,7 @@ template <int NCH, int CAP, int NW>
 int launch_front(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const uint32_t* list,
                  const unsigned int* n_list, unsigned int n_upper, uint32_t* overflow, unsigned int* n_overflow,
                  unsigned int* queue_cursor, uint32_t* try_list, Counters* ctr, Rec* recs, uint32_t* pids,
-                 unsigned long long* item_minr, int32_t* item_minfof, int bank_stride, cudaStream_t stream) {
+                 unsigned long long* item_minr, int32_t* item_minfof, int bank_stride, int multi, cudaStream_t stream) {
     soap_handle* h = c->h;
     auto kern = k_tier_front<NCH, CAP, NW>;
     const size_t smem = sizeof(FrontSlot<CAP>) * NW;
@@ -539,7 +577,7 @@ int launch_front(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const u
     if (grid > need) grid = need < 1 ? 1 : need;
     LAUNCH_N(h, CAP <= 256 ? "k_tier_front<256>" : "k_tier_front<1024>", kern, grid, 32 * NW, smem, stream, c->v, ha, cfg,
              list, n_list, overflow, n_overflow, queue_cursor, try_list, ctr, recs, pids, item_minr, item_minfof,
-             bank_stride);
+             bank_stride, multi);
     return 0;
 }
 
@@ -584,19 +622,23 @@ int soap_tier_round(soap_chunk* c, const DevCfg& cfg, HaloArrays& ha, int tier, 
     const int cap = soap_tier_cap(tier);
     const int bank_stride = soap_bank_stride(cfg);
     const bool full = (cfg.flags & (PF_KIN | PF_KAPPA | PF_TENS)) != 0;
+    // several ladder rungs per solve only where no selection depends on the sphere it was computed in: an inclusive
+    // sphere's stellar tensors count every star loaded (aperture_properties.py:3579-3594), the iterative tensors
+    // use the sphere of the rung that committed them
+    const int multi = (cfg.n_ap == 0 && cfg.n_pj == 0 && !(cfg.flags & PF_ITER)) ? 1 : 0;
     Rec* recs = (Rec*)h->get("h_trecs", sizeof(Rec) * (size_t)n_upper * cap);
     uint32_t* pids = (uint32_t*)h->get("h_tpids", sizeof(uint32_t) * (size_t)n_upper * cap);
     ha.gbank = (double*)h->get("h_gbank", sizeof(double) * (size_t)bank_stride * ((size_t)n_upper + 1));
     if (!recs || !pids || !ha.gbank) return -1;
 #define FRONT(NCH, CAP, NW)                                                                                            \
     launch_front<NCH, CAP, NW>(c, cfg, ha, list, n_list, n_upper, overflow, n_overflow, queue_cursor, try_list, ctr, recs, \
-                               pids, item_minr, item_minfof, bank_stride, stream)
+                               pids, item_minr, item_minfof, bank_stride, multi, stream)
     int rc;
     if (cfg.dmo) rc = tier == 0 ? FRONT(2, 256, 8) : FRONT(2, 1024, 8);
     else rc = tier == 0 ? FRONT(8, 256, 8) : FRONT(8, 1024, 8);
 #undef FRONT
     if (rc) return -1;
-    if (soap_launch_solve_seq(c, cfg, ha, try_list, &ctr->n_try, n_upper, recs, next, n_next, ctr, item_minr, item_minfof, stream))
+    if (soap_launch_solve_seq(c, cfg, ha, try_list, &ctr->n_try, n_upper, recs, next, n_next, ctr, item_minr, item_minfof, multi, stream))
         return -1;
 #define MOMS(V, NTY) launch_tier_moments<V, NTY>(c, cfg, ha, try_list, &ctr->n_try, n_upper, pids, bank_stride, stream)
     if (full && !cfg.dmo) rc = MOMS(V_FULL, 4);

@@ -413,11 +413,16 @@ def volume_catalogue(n_part, n_halos, boxsize, seed=20261018, m_part=0.0843, min
         return conc, mu_c, mu_o, np.floor((mu_o / mu_c - 1.0) * nh).astype(np.int64)
 
     conc, mu_c, mu_o, n_out = outskirts(nh)
+    # fit the particle budget like nfw_chunk: the halos that do not fit become copies of the largest that does
     budget = int(halo_fraction * n_part)
-    while int((nh + n_out).sum()) > budget:  # shave the most massive halos until the budget fits
-        k = int(np.argmax(np.cumsum((nh + n_out)[::-1])[::-1] <= budget)) or 1
-        nh[:k] = np.maximum(nh[:k] // 2, min_np)
+    csum = np.cumsum((nh + n_out)[::-1])[::-1]  # particles in halos i..end
+    keep_from = int((csum > budget).sum())
+    if keep_from > 0:
+        nh[:keep_from] = nh[min(keep_from, n_halos - 1)]
         conc, mu_c, mu_o, n_out = outskirts(nh)
+        while int((nh + n_out).sum()) > n_part and nh.max() > min_np:
+            nh = np.maximum(nh // 2, min_np)
+            conc, mu_c, mu_o, n_out = outskirts(nh)
     tot = nh + n_out
     start = np.cumsum(tot) - tot
     n_in_halos = int(tot.sum())
