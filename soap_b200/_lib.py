@@ -205,7 +205,8 @@ def default_handle(device=0):
     return h
 
 
-def cur_stream_ptr():
+def cur_stream_ptr(device=None):
+    """torch's current stream ON ``device`` (a chunk / handle on cuda:1 must not be handed the stream of cuda:0)"""
     import torch
 
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

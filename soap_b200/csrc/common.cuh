@@ -87,6 +87,17 @@ struct soap_handle {
     int64_t launches = 0;
     bool ktime = false;
     KernelLog klog;
+    // side streams for kernels of one phase that work on disjoint halos (fork / join around them with events)
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    int side_init() {
+        if (side[0]) return 0;
+        for (int i = 0; i < 3; i++) {
+            if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return -1;
+            if (cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+        }
+        return cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess ? 0 : -1;
+    }
     std::map<std::string, WsBuf> ws;
     // returns nullptr on failure (error string set)
     void* get(const char* name, size_t bytes) {

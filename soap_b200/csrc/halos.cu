@@ -59,6 +59,8 @@ constexpr int FINE_TARGET = 12;  // expected records per fine radial bin (sorted
 constexpr uint32_t SCAN_BIG = 32768;  // halos with more records are scanned by a CTA cluster
 constexpr uint32_t SEQ_MAX = 512;     // halos with up to this many records are scanned by one thread each (seq.cuh)
 constexpr int SCAN_CS = 8;            // CTAs per cluster for those
+constexpr uint32_t SCAN_HUGE = 524288;  // above this a cluster of 16 CTAs (non-portable size, B200 supports it)
+constexpr int SCAN_CS_HUGE = 16;
 // halos with up to this many bound particles start in tier 0 / 1 of the staged small-halo path (tier.cu:
 // spheres of up to 256 / 1024 particles); larger ones take the general path
 constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 500;
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
                                               uint32_t* __restrict__ acc_list,
                                               uint32_t* __restrict__ multi_list,
                                               uint32_t* __restrict__ seq_list,
+                                              uint32_t* __restrict__ huge_list,
                                               uint32_t* __restrict__ next, Counters* ctr,
                                               const double* __restrict__ item_msum) {
     unsigned int it = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +342,8 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
         ha.msum[h] = mcum;
         ha.rung_r[h] = ha.cur_r[h];
         const uint32_t cnt = ha.cnt[h];
-        if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // scanned by a CTA cluster
+        if (cnt > SCAN_HUGE) huge_list[atomicAdd(&ctr->n_huge, 1u)] = h;  // scanned by a cluster of 16 CTAs
+        else if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // by a cluster of 8
         else if (cnt <= SEQ_MAX) seq_list[atomicAdd(&ctr->n_seq, 1u)] = h;  // by one thread
         else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
         acc_list[atomicAdd(&ctr->n_acc, 1u)] = h;  // every accepted halo: its sweep is planned again
@@ -790,8 +794,24 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ?
                  const unsigned long long* __restrict__ item_minr,
                  const int32_t* __restrict__ item_minfof) {
     __shared__ ScanShared<NCH, SCAN_NT> S;
-    const unsigned int cid = blockIdx.x / CS, ncl = gridDim.x / CS;
-    for (unsigned int it = cid; it < *n_try; it += ncl) {
+    __shared__ unsigned int s_it;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int n_list = *n_try;
+    // dynamic queue: the lists are roughly largest-first, and a cluster that drew a 5-million-record halo must not
+    // also own every 37th of the rest
+    unsigned int* cursor = &ctr->scan_cursor[CS > 8 ? 2 : (CS > 1 ? 1 : 0)];
+    while (true) {
+        if (CS > 1) {
+            if (cluster.block_rank() == 0 && threadIdx.x == 0) s_it = atomicAdd(cursor, 1u);
+            cluster.sync();
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_it = atomicAdd(cursor, 1u);
+            __syncthreads();
+        }
+        const unsigned int it = CS > 1 ? *cluster.map_shared_rank(&s_it, 0) : s_it;
+        if (CS > 1) cluster.sync();  // everyone has read it before rank 0 draws again
+        if (it >= n_list) break;
         const uint32_t h = try_list[it];
         const uint32_t ib = ha.item_base[h];
         scan_solve_halo<NCH, CS, SCAN_NT, (CS > 1 ? 2 * SCAN_K : SCAN_K)>(S, ha, cfg, h, ha.cnt[h], recs + ha.rec_off[h], next, ctr,
@@ -983,6 +1003,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(rung_msum, double, h, "h_rung_msum", (size_t)H * LOOK_MAX); ha.rung_msum = rung_msum;
     WS_GET(multi_list, uint32_t, h, "h_multi", H);
     WS_GET(seq_list, uint32_t, h, "h_seq", H);
+    WS_GET(huge_list, uint32_t, h, "h_huge", H);
     WS_GET(bank_off, unsigned long long, h, "h_bank_off", H); ha.bank_off = bank_off;
     WS_GET(cuts_arr, Cuts, h, "h_cuts", H); ha.cuts = cuts_arr;
     ha.gbank = nullptr;
@@ -1113,7 +1134,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
-               acc_list, multi_list, seq_list, next, ctr, item_msum);
+               acc_list, multi_list, seq_list, huge_list, next, ctr, item_msum);
         log.end(stream);
         Counters hc;
         CUDA_TRY(cudaMemcpyAsync(&hc, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -1121,8 +1142,8 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
-        if (hc.n_try + hc.n_big + hc.n_seq > 0) {
-            const unsigned int n_try = hc.n_try + hc.n_big + hc.n_seq;
+        if (hc.n_try + hc.n_big + hc.n_seq + hc.n_huge > 0) {
+            const unsigned int n_try = hc.n_try + hc.n_big + hc.n_seq + hc.n_huge;
             // the accepted radius is generally smaller than the swept one: plan its sweep
             log.begin("plan", stream);
             if (plan(acc_list, &ctr->n_acc, n_try, look, 1)) return -1;
@@ -1181,27 +1202,52 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             }
             log.end(stream);
             log.begin("scan_solve", stream);
-            if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr, item_minfof,
-                                      0, stream))
-                return -1;
-            if (hc.n_try > 0) {
-                unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
-                if (cfg->dmo)
-                    LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next,
-                           ctr, item_minr, item_minfof);
-                else
-                    LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, stream, ha, dc, try_list, n_try_dev, recs, next,
-                           ctr, item_minr, item_minfof);
-            }
-            if (hc.n_big > 0) {
-                // one cluster of SCAN_CS CTAs per large halo
-                unsigned int ncl = hc.n_big < (unsigned)(sm * 2 / SCAN_CS) ? hc.n_big : (unsigned)(sm * 2 / SCAN_CS);
-                if (cfg->dmo)
-                    LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, stream, ha, dc, big_list,
-                           &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
-                else
-                    LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, stream, ha, dc, big_list,
-                           &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+            {
+                // the four scan kernels work on disjoint halos (by record count): thread per halo, CTA per halo,
+                // clusters of 8 and of 16 CTAs.  Forked onto side streams they overlap -- the giants' clusters keep a
+                // few SMs busy for milliseconds while the rest of the GPU does everything else.
+                if (h->side_init()) SOAP_FAIL("soap_process_halos: cannot create side streams");
+                CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
+                for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
+                if (hc.n_huge > 0) {
+                    // clusters of 16 CTAs (non-portable size): the largest halo is the critical path of this phase
+                    unsigned int ncl = hc.n_huge < (unsigned)(sm / SCAN_CS_HUGE) ? hc.n_huge : (unsigned)(sm / SCAN_CS_HUGE);
+                    if (cfg->dmo) {
+                        CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<2, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                        LAUNCH(h, (k_scan_solve<2, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, h->side[0], ha, dc, huge_list,
+                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
+                    } else {
+                        CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<8, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                        LAUNCH(h, (k_scan_solve<8, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, h->side[0], ha, dc, huge_list,
+                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
+                    }
+                }
+                if (hc.n_big > 0) {
+                    // one cluster of SCAN_CS CTAs per large halo
+                    unsigned int ncl = hc.n_big < (unsigned)(sm * 2 / SCAN_CS) ? hc.n_big : (unsigned)(sm * 2 / SCAN_CS);
+                    if (cfg->dmo)
+                        LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, h->side[1], ha, dc, big_list,
+                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+                    else
+                        LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, h->side[1], ha, dc, big_list,
+                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+                }
+                if (hc.n_try > 0) {
+                    unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
+                    if (cfg->dmo)
+                        LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, h->side[2], ha, dc, try_list, n_try_dev, recs, next,
+                               ctr, item_minr, item_minfof);
+                    else
+                        LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, h->side[2], ha, dc, try_list, n_try_dev, recs, next,
+                               ctr, item_minr, item_minfof);
+                }
+                if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr,
+                                          item_minfof, 0, stream))
+                    return -1;
+                for (int i = 0; i < 3; i++) {
+                    CUDA_TRY(cudaEventRecord(h->ev_join[i], h->side[i]));
+                    CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i], 0));
+                }
             }
             log.end(stream);
             log.begin("moments", stream);

@@ -182,6 +182,7 @@ struct Counters {
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
     unsigned int n_mslot, items_overflow, n_bslot, n_seq;
+    unsigned int scan_cursor[3], n_huge;  // dynamic queues of k_scan_solve (CTA / cluster of 8 / cluster of 16 lists)
     unsigned long long pairs, candidates, count_pairs, mom_pairs;
 };
 

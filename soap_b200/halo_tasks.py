@@ -245,7 +245,7 @@ class DeviceChunk:
         self.ptr = C.c_void_p()
         _lib.check(
             _lib.lib().soap_chunk_create(
-                self.handle.ptr, arr, n_types, self.boxsize, int(fine_ppc), C.byref(self.ptr), _lib.cur_stream_ptr()
+                self.handle.ptr, arr, n_types, self.boxsize, int(fine_ppc), C.byref(self.ptr), _lib.cur_stream_ptr(self.device)
             )
         )
         # the SoA copy lives in the chunk; the staging tensors can go
@@ -373,7 +373,7 @@ def process_halos(chunk: DeviceChunk, cfg: HaloPropConfig, halo_arrays, out=None
             C.c_void_p(table.data_ptr()),
             ncol,
             C.c_void_p(status.data_ptr()),
-            _lib.cur_stream_ptr(),
+            _lib.cur_stream_ptr(dev),
         )
     )
     return HaloResults(table, status, cols, cfg)

@@ -30,7 +30,7 @@ def box_wrap(pos, ref_pos, boxsize, handle=None):
     ref = (C.c_double * 3)(*[float(x) for x in ref_pos])
     _lib.check(
         _lib.lib().soap_box_wrap(
-            h.ptr, C.c_void_p(pos.data_ptr()), pos.shape[0], ref, float(boxsize), _lib.cur_stream_ptr()
+            h.ptr, C.c_void_p(pos.data_ptr()), pos.shape[0], ref, float(boxsize), _lib.cur_stream_ptr(pos.device)
         )
     )
     return pos
@@ -96,7 +96,7 @@ class SharedMesh:
                 C.c_void_p(self.cell_offset.data_ptr()),
                 C.c_void_p(self.sort_idx.data_ptr()),
                 1 if stable else 0,
-                _lib.cur_stream_ptr(),
+                _lib.cur_stream_ptr(self.device),
             )
         )
         self.pos_min = np.array(pmin[:], dtype=np.float64)
@@ -155,7 +155,7 @@ class SharedMesh:
                     C.c_void_p(idx.data_ptr() if idx is not None else 0),
                     mptr,
                     eptr,
-                    _lib.cur_stream_ptr(),
+                    _lib.cur_stream_ptr(self.device),
                 )
             )
 
