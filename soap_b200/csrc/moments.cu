@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = TB / 32;
     constexpr int VP = BankAcc<V>::VP;
+    constexpr int NCOPY = BankAcc<V>::HALF ? 2 * NW : NW;  // private bank copies of the CTA (priv)
     double* banks = (double*)smem_raw;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* stage_w = banks + (size_t)(priv ? NW : 1) * gbank_stride + (size_t)wid * 32 * VP;
-    int* skey_w = (int*)(banks + (size_t)(priv ? NW : 1) * gbank_stride + (size_t)NW * 32 * VP) + wid * 32;
-    double* bank_w = banks + (priv ? (size_t)wid * gbank_stride : 0);
+    double* stage_w = banks + (size_t)(priv ? NCOPY : 1) * gbank_stride + (size_t)wid * 32 * VP;
+    int* skey_w = (int*)(banks + (size_t)(priv ? NCOPY : 1) * gbank_stride + (size_t)NW * 32 * VP) + wid * 32;
+    double* bank_w = banks + (priv ? (size_t)wid * (NCOPY / NW) * gbank_stride : 0);
     __shared__ SweepShared SW;
     __shared__ Cuts cuts;
     const unsigned int n_items = *n_items_dev;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         const int ncut = cuts.n;
         const int nbank = (ncut + 1) * 2 * NTY;
         if (priv) {
-            for (int w = 0; w < NW; w++)
+            for (int w = 0; w < NCOPY; w++)
                 for (int i = threadIdx.x; i < nbank * V; i += TB) banks[(size_t)w * gbank_stride + i] = 0.0;
         } else {
             for (int i = threadIdx.x; i < nbank * V; i += TB) banks[i] = 0.0;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         __syncthreads();
         const int32_t cen_fof = sr->cen_fof;
         BankAcc<V> ba;
-        ba.init();
+        ba.init(gbank_stride);
         sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             bool in = false;
             int key = 0;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         if (priv) {
             for (int i = threadIdx.x; i < nbank * V; i += TB) {
                 double s = banks[i];
-                for (int w = 1; w < NW; w++) s += banks[(size_t)w * gbank_stride + i];
+                for (int w = 1; w < NCOPY; w++) s += banks[(size_t)w * gbank_stride + i];
                 banks[i] = s;
             }
             __syncthreads();
@@ -266,9 +267,10 @@ int soap_launch_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     const int stride = (cfg.n_so + cfg.n_ap + 3) * 2 * nty * V;
     const int NW = TB / 32, VP = V | 1;
     const size_t stage_bytes = (size_t)NW * 32 * VP * sizeof(double) + (size_t)NW * 32 * sizeof(int);
-    // warp-private banks when they fit next to the staging tiles
-    const int priv = ((size_t)NW * stride * sizeof(double) + stage_bytes <= 96 * 1024) ? 1 : 0;
-    const size_t smem = (size_t)(priv ? NW : 1) * stride * sizeof(double) + stage_bytes;
+    // warp-private banks when they fit next to the staging tiles (V <= 16: one copy per half-warp, always private)
+    const int ncopy = V <= 16 ? 2 * NW : NW;
+    const int priv = (V <= 16 || (size_t)ncopy * stride * sizeof(double) + stage_bytes <= 96 * 1024) ? 1 : 0;
+    const size_t smem = (size_t)(priv ? ncopy : 1) * stride * sizeof(double) + stage_bytes;
     if (smem > 220 * 1024) SOAP_FAIL("soap_process_halos: %d SO + %d aperture variations need %zu bytes of shared memory", cfg.n_so, cfg.n_ap, smem);
     unsigned int g = n_items_host < grid ? n_items_host : grid;
     if (g < 1) g = 1;

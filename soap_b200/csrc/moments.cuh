@@ -227,14 +227,22 @@ template <int V>
 struct BankAcc {
     static constexpr int NA = (V + 31) / 32;
     static constexpr int VP = V | 1;  // odd row stride: conflict-free 64-bit stores
+    // V <= 16: two staged particles are added per step, one by each half-warp (lane & 15 = term), into the
+    // half-warp's OWN copy of the banks (bank_w holds two copies, `hstride` doubles apart: callers add them up).
+    // Plain read-modify-write, no running sums, no flush on a key change -- in cell order the (shell, bound) key
+    // changes with almost every particle, and flushing 15 running sums each time was most of this kernel.
+    static constexpr bool HALF = V <= 16;
     double acc[NA];
     int cur;
-    __device__ __forceinline__ void init() {
+    int hstride;
+    __device__ __forceinline__ void init(int half_stride = 0) {
         cur = -1;
+        hstride = half_stride;
 #pragma unroll
         for (int q = 0; q < NA; q++) acc[q] = 0.0;
     }
     __device__ __forceinline__ void flush(double* bank_w, int priv, int lane) {
+        if (HALF) return;
         if (cur >= 0) {
             double* b = bank_w + (size_t)cur * V;
 #pragma unroll
@@ -261,6 +269,17 @@ struct BankAcc {
         }
         __syncwarp();
         const int cnt = __popc(bal);
+        if (HALF) {
+            const int half = lane >> 4, t = lane & 15;
+            double* b = bank_w + (size_t)half * hstride;
+            if (t < V)
+                for (int p = half; p < cnt; p += 2) {
+                    double* e = b + (size_t)skey_w[p] * V + t;
+                    *e += stage_w[p * VP + t];
+                }
+            __syncwarp();
+            return;
+        }
         for (int p = 0; p < cnt; p++) {
             const int k = skey_w[p];
             if (k != cur) { flush(bank_w, priv, lane); cur = k; }

@@ -480,11 +480,13 @@ __global__ void __launch_bounds__(32 * NW) k_tier_moments(ChunkView v, HaloArray
         const int nbank = (ncut + 1) * 2 * NTY;
         double* gb = ha.gbank + ha.bank_off[h];
         double* banks = smem_banks ? sbank : gb;
-        for (int i = lane; i < nbank * V; i += 32) banks[i] = 0.0;
+        constexpr int NCOPY = BankAcc<V>::HALF ? 2 : 1;  // V <= 16: one copy per half-warp (always in shared memory)
+        const int hstride = nbank * V;
+        for (int i = lane; i < NCOPY * nbank * V; i += 32) banks[i] = 0.0;
         __syncwarp();
         const int32_t cen_fof = ha.sres[h].cen_fof;
         BankAcc<V> ba;
-        ba.init();
+        ba.init(hstride);
         for (uint32_t b0 = 0; b0 < n; b0 += 32) {
             const uint32_t i = b0 + lane;
             const bool in = i < n;
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(32 * NW) k_tier_moments(ChunkView v, HaloArray
         ba.flush(banks, 1, lane);
         __syncwarp();
         if (smem_banks)
-            for (int i = lane; i < nbank * V; i += 32) gb[i] = sbank[i];
+            for (int i = lane; i < nbank * V; i += 32) gb[i] = NCOPY == 2 ? sbank[i] + sbank[hstride + i] : sbank[i];
         __syncwarp();
     }
 }
@@ -589,9 +591,10 @@ int launch_tier_moments(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, 
     constexpr int NW = 8;
     const size_t bank_bytes = (size_t)bank_stride * sizeof(double);
     // banks in shared memory while a CTA of 8 warps stays below ~48 KB; else straight in global memory
-    // (touched only on a key change)
-    const int smem_banks = bank_bytes <= 4096 ? 1 : 0;
-    const size_t slot = (sizeof(MomSlot<V>) + (smem_banks ? bank_bytes : 0) + 15) & ~(size_t)15;
+    // (touched only on a key change).  The 15-term set keeps one copy per half-warp, always in shared memory.
+    const int ncopy = V <= 16 ? 2 : 1;
+    const int smem_banks = (V <= 16 || bank_bytes <= 4096) ? 1 : 0;
+    const size_t slot = (sizeof(MomSlot<V>) + (smem_banks ? ncopy * bank_bytes : 0) + 15) & ~(size_t)15;
     const size_t smem = slot * NW;
     auto kern = k_tier_moments<V, NTY, NW>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
