@@ -78,7 +78,9 @@ KERNEL_MODEL = {
     "k_fine_hist_halo": (24, "rec"),
     "k_collect": (49, "rec"),              # 33 in, 16 record out
     "k_sort_bins": (32, "rec"),            # 16 in, 16 out
-    "k_scan_solve": (16, "rec"),
+    "k_scan_solve<1>": (16, "rec"),        # CTA per halo; <8> / <16>: clusters of 8 / 16 CTAs per halo (the three run
+    "k_scan_solve<8>": (16, "rec"),        # concurrently on side streams, each on its own size class of halos: their
+    "k_scan_solve<16>": (16, "rec"),       # times overlap and are not additive)
     "k_moments": (48, "mom"),              # position 24, mass 4, velocity 12, grnr 4, fof 4
     "k_projected": (48, "mom"),
     "k_kappa": (48, "mom"),
@@ -91,6 +93,8 @@ def kernel_key(name):
     n = name.strip("() ")
     if n in KERNEL_MODEL:
         return n
+    if n.startswith("k_scan_solve<"):  # k_scan_solve<NCH, CS>: one entry per cluster size
+        return "k_scan_solve<%s>" % n.split(",")[-1].strip(" >").replace("SCAN_CS_HUGE", "16").replace("SCAN_CS", "8")
     return n.split("<")[0]
 
 

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(TB) k_gather(TypesIn in, const uint32_t* __res
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n) return;
     const uint32_t src = perm[d];
+    SOAP_ASSERT(src < n);
     int ti = 0;
 #pragma unroll
     for (int k = 1; k < 4; k++)

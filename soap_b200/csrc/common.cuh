@@ -159,6 +159,20 @@ static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {
 // ------------------------------------------------------------------ device
 #ifdef __CUDACC__
 
+// Device-side assertions of the checked build (make checked): an index that leaves its array traps the kernel
+// and names the line, instead of corrupting a neighbour silently.  Compiled out of the product build.
+#ifdef SOAP_CHECKS
+#define SOAP_ASSERT(cond)                                                              \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            printf("SOAP_ASSERT failed: %s:%d: %s\n", __FILE__, __LINE__, #cond);      \
+            __trap();                                                                  \
+        }                                                                              \
+    } while (0)
+#else
+#define SOAP_ASSERT(cond) ((void)0)
+#endif
+
 // numpy floored modulo for positive divisor L (npy_divmod): fmod, then shift
 // negative remainders by L (the sum is rounded, so tiny negatives give L).
 static __device__ __noinline__ double floored_mod_generic(double a, double L) {

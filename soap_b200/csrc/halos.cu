@@ -547,9 +547,11 @@ __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevC
                 unsigned base = 0;
                 if (lane == 0 && bal) base = atomicAdd(cursor, (unsigned)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
+                SOAP_ASSERT(!in || base + __popc(bal & ((1u << lane) - 1u)) < ha.cnt[h]);
                 if (in) out[base + __popc(bal & ((1u << lane) - 1u))] = rec;
             } else if (in) {
                 unsigned slot = atomicAdd(&fcur[fb], 1u);
+                SOAP_ASSERT(fb < nf && (unsigned long long)fex[fb] + slot < (unsigned long long)fex[fb + 1]);
                 out[(unsigned long long)fex[fb] + slot] = rec;
             }
         });

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
                                            (double)v.vy[t], (double)v.vz[t], v.grnr[t], hidx, v.fof[t], cen_fof,
                                            NTY == 1 ? 1u : (uint32_t)v.type[t], val);
             }
+            SOAP_ASSERT(!in || (key >= 0 && key < nbank));
             ba.add(in, key, val, stage_w, skey_w, bank_w, priv, lane);
         });
         ba.flush(bank_w, priv, lane);

@@ -605,6 +605,7 @@ __device__ void solve_seq_halo(const HaloArrays& ha, const DevCfg& cfg, const ui
         while (j + 1 < look && required == 0.0) {
             j++;
             const uint32_t nj = ha.rung_cnt[(size_t)h * LOOK_MAX + j];
+            SOAP_ASSERT(nj <= n_all && nj >= n);
             // the radial order must agree with the rung binning at the prefix boundary (the two come from
             // different roundings of the same distance)
             const bool ok = (nj == 0 || (int)((ld_rec(R + nj - 1).flags >> 4) & 15u) <= j) &&

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                                                         uint32_t* __restrict__ try_list, Counters* ctr,
                                                         Rec* __restrict__ recs, uint32_t* __restrict__ pids,
                                                         unsigned long long* __restrict__ item_minr,
-                                                        int32_t* __restrict__ item_minfof, int bank_stride, int multi) {
+                                                        int32_t* __restrict__ item_minfof, int bank_stride, int multi,
+                                                        unsigned long long rec_capacity) {
     constexpr uint32_t CAND_MAX = 16u * CAP;  // larger sweeps belong to the CTA-wide kernels of the general path
     constexpr int U = 4;                      // candidate groups in flight per warp (memory-level parallelism)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
 #pragma unroll
                     for (int k = 0; k < 3; k++) rung += (k + 1 < n_rungs && !(r2 <= r2rung[k])) ? 1u : 0u;
                     rc.flags = tc | ((v.grnr[t] == hidx) ? 4u : 0u) | (rung << 4);
+                    SOAP_ASSERT(slot < (uint32_t)CAP && slot < n && t < (uint32_t)v.n && rung < 4u);
                     W.rec[slot] = rc;
                     W.pid[slot] = t;
                     const int32_t f = (int32_t)v.fof[t];
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                 __syncwarp();
                 for (uint32_t i = lane; i < n; i += 32) {
                     const uint32_t pos = atomicAdd(&W.bin_off[bin_of(W.rec[i].rbits)], 1u);
+                    SOAP_ASSERT(pos < n);
                     W.ord[pos] = (uint16_t)i;
                 }
                 __syncwarp();
@@ -431,8 +434,10 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
             try_list[atomicAdd(&ctr->n_try, 1u)] = h;
         }
         off = __shfl_sync(0xffffffffu, off, 0);
+        SOAP_ASSERT(W.n_stage == n);  // the gather found exactly the particles the count sweep counted
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t o = W.ord[i];
+            SOAP_ASSERT(o < n && off + i < rec_capacity);
             recs[off + i] = W.rec[o];
             pids[off + i] = W.pid[o];
         }
@@ -494,6 +499,7 @@ __global__ void __launch_bounds__(32 * NW) k_tier_moments(ChunkView v, HaloArray
             double val[V];
             if (in) {
                 const uint32_t t = pid[i];
+                SOAP_ASSERT(t < (uint32_t)v.n);
                 const double x = rewrap_rel(v.px[t], cx, L, halfL);
                 const double y = rewrap_rel(v.py[t], cy, L, halfL);
                 const double z = rewrap_rel(v.pz[t], cz, L, halfL);
@@ -501,6 +507,7 @@ __global__ void __launch_bounds__(32 * NW) k_tier_moments(ChunkView v, HaloArray
                 key = moment_terms<V, NTY>(W.cuts, ncut, cfg, x, y, z, r, (double)v.mass[t], (double)v.vx[t],
                                            (double)v.vy[t], (double)v.vz[t], v.grnr[t], hidx, v.fof[t], cen_fof,
                                            NTY == 1 ? 1u : (uint32_t)v.type[t], val);
+                SOAP_ASSERT(key >= 0 && key < nbank);
             }
             ba.add(in, key, val, W.stage, W.skey, banks, 1, lane);
         }
@@ -579,7 +586,7 @@ int launch_front(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const u
     if (grid > need) grid = need < 1 ? 1 : need;
     LAUNCH_N(h, CAP <= 256 ? "k_tier_front<256>" : "k_tier_front<1024>", kern, grid, 32 * NW, smem, stream, c->v, ha, cfg,
              list, n_list, overflow, n_overflow, queue_cursor, try_list, ctr, recs, pids, item_minr, item_minfof,
-             bank_stride, multi);
+             bank_stride, multi, (unsigned long long)n_upper * CAP);
     return 0;
 }
 
