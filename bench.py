@@ -71,16 +71,16 @@ KERNEL_MODEL = {
     "k_gather": (102, "part"),             # 4 permutation + 49 payload in, 49 out
     "k_tier_front<256>": (57, "tier0"),    # 24 position + 4 mass + 4 grnr + 4 fof + 1 type in, 16 record + 4 slot out
     "k_tier_front<1024>": (57, "tier1"),
-    "k_solve_seq": (16, "tier"),           # one read of the sorted records
+    "k_solve_seq": (16, "seq"),            # one read of the sorted records (tier halos + the smallest general-path ones)
     "k_tier_moments": (52, "tier"),        # 4 slot + 48 payload
     "k_rows": (None, "halo"),              # ncol * 8 out, filled in at run time
     "k_count": (28, "count"),              # position 24 + mass 4
     "k_fine_hist_halo": (24, "rec"),
     "k_collect": (49, "rec"),              # 33 in, 16 record out
     "k_sort_bins": (32, "rec"),            # 16 in, 16 out
-    "k_scan_solve<1>": (16, "rec"),        # CTA per halo; <8> / <16>: clusters of 8 / 16 CTAs per halo (the three run
-    "k_scan_solve<8>": (16, "rec"),        # concurrently on side streams, each on its own size class of halos: their
-    "k_scan_solve<16>": (16, "rec"),       # times overlap and are not additive)
+    "k_scan_solve<1>": (16, "rec_cta"),        # CTA per halo; <8> / <16>: clusters of 8 / 16 CTAs per halo (the three run
+    "k_scan_solve<8>": (16, "rec_c8"),        # concurrently on side streams, each on its own size class of halos: their
+    "k_scan_solve<16>": (16, "rec_c16"),       # times overlap and are not additive)
     "k_moments": (48, "mom"),              # position 24, mass 4, velocity 12, grnr 4, fof 4
     "k_projected": (48, "mom"),
     "k_kappa": (48, "mom"),
@@ -648,6 +648,8 @@ def main():
         "part": float(n_part), "tier0": stats.get("small_pairs_0", 0.0), "tier1": stats.get("small_pairs_1", 0.0),
         "tier": stats.get("small_pairs", 0.0), "count": stats.get("count_pairs", 0.0), "rec": stats.get("try_pairs", 0.0),
         "mom": stats.get("moment_pairs", 0.0), "halo": float(H),
+        "seq": stats.get("small_pairs", 0.0) + stats.get("rec_seq", 0.0), "rec_cta": stats.get("rec_cta", 0.0),
+        "rec_c8": stats.get("rec_cluster8", 0.0), "rec_c16": stats.get("rec_cluster16", 0.0),
     }
     kernels = {}
     for name, (n_l, t_ms) in ktimes.items():

@@ -275,6 +275,10 @@ int64_t soap_chunk_timings(const soap_chunk* c, char* buf, int64_t buflen) {
              (long long)c->last_small_pairs, (long long)c->last_tier_pairs[0], (long long)c->last_tier_pairs[1],
              (long long)c->last_tier_pairs[2]);
     s += line;
+    snprintf(line, sizeof(line), "stat/rec_seq:%lld\nstat/rec_cta:%lld\nstat/rec_cluster8:%lld\nstat/rec_cluster16:%lld\n",
+             (long long)c->last_rec_class[0], (long long)c->last_rec_class[1], (long long)c->last_rec_class[2],
+             (long long)c->last_rec_class[3]);
+    s += line;
     int64_t m = (int64_t)s.size() < buflen - 1 ? (int64_t)s.size() : buflen - 1;
     memcpy(buf, s.data(), m);
     buf[m] = 0;

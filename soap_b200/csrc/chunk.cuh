@@ -79,6 +79,7 @@ struct soap_chunk {
     int64_t last_tier_pairs[3] = {0, 0, 0};
     int64_t last_candidates = 0;
     int64_t last_count_pairs = 0, last_try_pairs = 0, last_mom_pairs = 0;
+    int64_t last_rec_class[4] = {0, 0, 0, 0};
     int last_rounds = 0;
     PhaseLog create_log, halo_log;
     int type_present[4] = {0, 0, 0, 0};

@@ -244,27 +244,28 @@ __global__ void __launch_bounds__(PLAN_NT) k_plan_items(ChunkView v, HaloArrays 
 // shared_mesh.py:122-200), for the next ha.look[h] ladder rungs in one sweep:
 // the sphere of the furthest rung is swept once and every particle is binned by
 // the first rung whose radius includes it (the same r2 <= radius^2 test).
+template <int NLOOK>
 __global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, const Item* __restrict__ items,
                                               Counters* ctr, double* __restrict__ item_msum) {
     __shared__ SweepShared S;
-    __shared__ unsigned int s_cnt[TB / 32][LOOK_MAX];
-    __shared__ double s_m[TB / 32][LOOK_MAX];
+    __shared__ unsigned int s_cnt[TB / 32][NLOOK];
+    __shared__ double s_m[TB / 32][NLOOK];
     const unsigned int n_items = ctr->n_items;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const Item im = items[it];
         const uint32_t h = im.halo;
         const double cx = ha.cofp[3 * h], cy = ha.cofp[3 * h + 1], cz = ha.cofp[3 * h + 2];
-        double rr[LOOK_MAX], r2k[LOOK_MAX];
-        const int nr = ladder_radii(ha.cur_r[h], ha.rr_in[h], ha.look[h], rr);
+        double rr[NLOOK], r2k[NLOOK];
+        const int nr = ladder_radii(ha.cur_r[h], ha.rr_in[h], ha.look[h] < NLOOK ? ha.look[h] : NLOOK, rr);
 #pragma unroll
-        for (int k = 0; k < LOOK_MAX; k++) r2k[k] = k < nr ? __dmul_rn(rr[k], rr[k]) : -1.0;
+        for (int k = 0; k < NLOOK; k++) r2k[k] = k < nr ? __dmul_rn(rr[k], rr[k]) : -1.0;
         const double r = rr[nr - 1];
         const double halfL = 0.5 * v.L, L = v.L;
-        unsigned int cnt[LOOK_MAX];
-        double msum[LOOK_MAX];
+        unsigned int cnt[NLOOK];
+        double msum[NLOOK];
 #pragma unroll
-        for (int k = 0; k < LOOK_MAX; k++) { cnt[k] = 0; msum[k] = 0.0; }
+        for (int k = 0; k < NLOOK; k++) { cnt[k] = 0; msum[k] = 0.0; }
         sweep_item(v, S, cx, cy, cz, r, im, [&](uint32_t t, bool ok) {
             if (ok) {
                 const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
@@ -272,13 +273,13 @@ __global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, con
                     const double m = (double)v.mass[t];
                     bool placed = false;
 #pragma unroll
-                    for (int k = 0; k < LOOK_MAX; k++)
+                    for (int k = 0; k < NLOOK; k++)
                         if (!placed && k < nr && r2 <= r2k[k]) { cnt[k]++; msum[k] += m; placed = true; }
                 }
             }
         });
 #pragma unroll
-        for (int k = 0; k < LOOK_MAX; k++) {
+        for (int k = 0; k < NLOOK; k++) {
             const unsigned int c = (unsigned int)warp_sum_u64(cnt[k]);
             const double m = warp_sum(msum[k]);
             if (lane == 0) { s_cnt[wid][k] = c; s_m[wid][k] = m; }
@@ -342,10 +343,12 @@ __global__ void __launch_bounds__(128) k_gate(HaloArrays ha, DevCfg cfg, const u
         ha.msum[h] = mcum;
         ha.rung_r[h] = ha.cur_r[h];
         const uint32_t cnt = ha.cnt[h];
-        if (cnt > SCAN_HUGE) huge_list[atomicAdd(&ctr->n_huge, 1u)] = h;  // scanned by a cluster of 16 CTAs
-        else if (cnt > SCAN_BIG) big_list[atomicAdd(&ctr->n_big, 1u)] = h;  // by a cluster of 8
-        else if (cnt <= SEQ_MAX) seq_list[atomicAdd(&ctr->n_seq, 1u)] = h;  // by one thread
-        else try_list[atomicAdd(&ctr->n_try, 1u)] = h;
+        int cls;
+        if (cnt > SCAN_HUGE) { huge_list[atomicAdd(&ctr->n_huge, 1u)] = h; cls = 3; }  // scanned by a cluster of 16 CTAs
+        else if (cnt > SCAN_BIG) { big_list[atomicAdd(&ctr->n_big, 1u)] = h; cls = 2; }  // by a cluster of 8
+        else if (cnt <= SEQ_MAX) { seq_list[atomicAdd(&ctr->n_seq, 1u)] = h; cls = 0; }  // by one thread
+        else { try_list[atomicAdd(&ctr->n_try, 1u)] = h; cls = 1; }
+        atomicAdd(&ctr->rec_class[cls], (unsigned long long)cnt);
         acc_list[atomicAdd(&ctr->n_acc, 1u)] = h;  // every accepted halo: its sweep is planned again
         ha.state[h] = ST_TRY;
         if (cnt <= SMALL_CAP) {
@@ -412,10 +415,11 @@ __global__ void __launch_bounds__(256) k_sort_bins(const int64_t* __restrict__ f
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long base = use_single_base ? ctr->rec_single : 0ull;  // multi region follows the single region
     const uint32_t nwarp = gridDim.x * 8;
-    for (uint32_t b = blockIdx.x * 8 + wid; b < n_fine; b += nwarp) {
+    // one bin of up to 32 / BIN_SMEM records by the whole warp
+    auto sort_bin = [&](uint32_t b) {
         const unsigned long long e0 = (unsigned long long)fine_excl[b];
         const uint32_t cnt = (uint32_t)((unsigned long long)fine_excl[b + 1] - e0);
-        if (cnt < 2) continue;
+        if (cnt < 2) return;
         Rec* g = recs + base + e0;
         if (cnt <= 32) {
             Rec mine;
@@ -463,6 +467,41 @@ __global__ void __launch_bounds__(256) k_sort_bins(const int64_t* __restrict__ f
             bk.halo = 0;
             if (cnt <= SB_CAP) bkt_big[atomicAdd(&ctr->n_bkt_big, 1u)] = bk;
             else bkt_huge[atomicAdd(&ctr->n_bkt_huge, 1u)] = bk;
+        }
+    };
+    // bins are made for ~FINE_TARGET = 12 records: two of them share a warp, one per half-warp, with the 16-wide
+    // network (10 compare-exchange steps instead of 15, and half the warps); a pair with a fuller bin falls back
+    for (uint32_t b0 = 2 * (blockIdx.x * 8 + wid); b0 < n_fine; b0 += 2 * nwarp) {
+        const int half = lane >> 4, l16 = lane & 15;
+        const uint32_t b = b0 + half;
+        unsigned long long e0 = 0;
+        uint32_t cnt = 0;
+        if (b < n_fine) {
+            e0 = (unsigned long long)fine_excl[b];
+            cnt = (uint32_t)((unsigned long long)fine_excl[b + 1] - e0);
+        }
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, cnt, 16);
+        if (cnt <= 16 && other <= 16) {
+            Rec* g = recs + base + e0;
+            Rec mine;
+            if (l16 < (int)cnt) mine = g[l16];
+            else { mine.rbits = ~0ull; mine.m = 0.f; mine.flags = 0; }
+#pragma unroll
+            for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    Rec o;
+                    o.rbits = __shfl_xor_sync(0xffffffffu, mine.rbits, j);
+                    o.m = __shfl_xor_sync(0xffffffffu, mine.m, j);
+                    o.flags = __shfl_xor_sync(0xffffffffu, mine.flags, j);
+                    const bool take_min = ((l16 & k) == 0) == ((l16 & j) == 0);
+                    if (take_min ? (o.rbits < mine.rbits) : (mine.rbits < o.rbits)) mine = o;
+                }
+            }
+            if (l16 < (int)cnt && cnt > 1) g[l16] = mine;
+        } else {
+            sort_bin(b0);
+            if (b0 + 1 < n_fine) sort_bin(b0 + 1);
         }
     }
 }
@@ -1023,6 +1062,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     log.reset();
     c->last_pairs = 0;
     c->last_candidates = 0;
+    for (int k = 0; k < 4; k++) c->last_rec_class[k] = 0;
     c->last_rounds = 0;
     uint32_t* pend = listA;
     uint32_t* next = listB;
@@ -1132,7 +1172,10 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         if (plan(pend, n_pend_dev, n_pend, look, 0)) return -1;
         log.end(stream);
         log.begin("count", stream);
-        LAUNCH(h, k_count, sweep_grid, TB, 0, stream, v, ha, items, ctr, item_msum);
+        // the first round's sweep covers 4 rungs, the stragglers' LOOK_MAX: two instantiations, so that the bulk does
+        // not carry twelve counters and mass sums per thread
+        if (look <= 4) LAUNCH(h, k_count<4>, sweep_grid, TB, 0, stream, v, ha, items, ctr, item_msum);
+        else LAUNCH(h, k_count<LOOK_MAX>, sweep_grid, TB, 0, stream, v, ha, items, ctr, item_msum);
         log.end(stream);
         log.begin("gate", stream);
         LAUNCH(h, k_gate, grid_for(n_pend, 128), 128, 0, stream, ha, dc, pend, n_pend_dev, try_list, big_list,
@@ -1144,6 +1187,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_cand += hc.candidates;
         total_count_pairs += hc.count_pairs;
         total_try_pairs += hc.rec_total;
+        for (int k = 0; k < 4; k++) c->last_rec_class[k] += (int64_t)hc.rec_class[k];
         if (hc.n_try + hc.n_big + hc.n_seq + hc.n_huge > 0) {
             const unsigned int n_try = hc.n_try + hc.n_big + hc.n_seq + hc.n_huge;
             // the accepted radius is generally smaller than the swept one: plan its sweep
@@ -1187,7 +1231,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
             log.begin("sort", stream);
             if (hc.n_multi > 0) {
                 // bins first: they feed the bucket lists of the CTA-wide kernels below
-                const unsigned int nb = (hc.n_fine + 7) / 8;
+                const unsigned int nb = (hc.n_fine + 15) / 16;  // 16 bins per CTA: two per warp
                 LAUNCH(h, k_sort_bins, nb < (unsigned)(sm * 8) ? nb : (unsigned)(sm * 8), 256, 0, stream, fine_excl,
                        hc.n_fine, ctr, 1, recs, bkt_big, bkt_huge);
             }
@@ -1284,7 +1328,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                         LAUNCH(h, k_pj_bins<true>, sweep_grid, TB, 0, stream, v, ha, dc, items, &ctr->n_items, pl, ax,
                                pcnt, pexcl, precs);
                         CUDA_TRY(cudaMemsetAsync(&ctr->n_bkt_small, 0, 3 * sizeof(unsigned int), stream));
-                        const unsigned int nb = (nfp + 7) / 8;
+                        const unsigned int nb = (nfp + 15) / 16;
                         LAUNCH(h, k_sort_bins, nb < (unsigned)(sm * 8) ? nb : (unsigned)(sm * 8), 256, 0, stream, pexcl,
                                nfp, ctr, 0, precs, bkt_big, bkt_huge);
                         LAUNCH(h, (k_sort_bucket<SB_CAP, 512>), (unsigned)(sm * 3), 512, SB_CAP * sizeof(Rec), stream,

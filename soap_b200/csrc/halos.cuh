@@ -184,6 +184,7 @@ struct Counters {
     unsigned int n_mslot, items_overflow, n_bslot, n_seq;
     unsigned int scan_cursor[3], n_huge;  // dynamic queues of k_scan_solve (CTA / cluster of 8 / cluster of 16 lists)
     unsigned long long pairs, candidates, count_pairs, mom_pairs;
+    unsigned long long rec_class[4];  // records of the halos scanned by: thread, CTA, cluster of 8, cluster of 16
 };
 
 #ifdef __CUDACC__
