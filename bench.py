@@ -56,6 +56,7 @@ M_PART = {"config4": 0.0843 * (25.0 / 284.4) ** 3 * 512**3 / (2 * 376**3)}
 HYDRO_TYPES = {0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001}
 SEED = 20261018
 SO_LIST = None  # filled in main (needs synth)
+VOLUME_SLABS = 256  # slabs per dimension of the ghost-shell cover of the one-volume runs (N > 1)
 CPU_SAMPLE_FRACTION = 0.05  # volume fraction of the fixed central sub-cube the CPU arm processes
 
 # Algorithmic bytes per unit of every kernel.  unit = which counter the kernel's work is
@@ -438,11 +439,11 @@ def main():
         from soap_b200 import chunk_tasks as ct
 
         Lv = L * world ** (1.0 / 3.0)
-        cat = synth.volume_catalogue(n_part * world, n_halos * world, Lv, seed=SEED, max_np=max_np)
+        cat = synth.volume_catalogue(n_part * world, n_halos * world, Lv, seed=SEED, max_np=max_np, bg_cells=VOLUME_SLABS)
         H_all = {k: cat[k] for k in ("cofp", "index", "search_radius", "read_radius", "nr_bound_part", "is_central")}
         hs, csz = ct.peano_decomposition(Lv, H_all, world)
         mine = ct.chunk_halos(hs, csz, ct.assign_chunks(len(csz), world)[rank][0])
-        data, halos = synth.volume_chunk(cat, mine["index"], device=gen_dev)
+        data, halos = synth.volume_chunk(cat, mine["index"], device=gen_dev, cells_per_dim=VOLUME_SLABS)
         n_own = int(sum(len(d["Masses"]) for d in data.values()))
         wl_name = (f"{args.workload} x {world}: ONE synthetic DMO volume, L={Lv:.1f} Mpc, {n_part * world} particles, "
                    f"{n_halos_total} halos, cut into {world} Peano-Hilbert chunks with ghost shells (slab cover of the read "
@@ -625,6 +626,18 @@ def main():
 
         run_e2e(min(args.warmup, 2))
         barrier()
+        # the host -> device copy of one chunk alone, all ranks at once: the ceiling the pipeline can reach when the
+        # copy is the longer of the two overlapped legs (N concurrent uploads share the host's memory system)
+        t0 = time.perf_counter()
+        tk = feed.upload(host, host_h)
+        tk[2].synchronize()
+        barrier()
+        copy_alone = time.perf_counter() - t0
+        del tk
+        tc = torch.tensor([copy_alone], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        copy_alone = float(tc.item())
         t0 = time.perf_counter()
         n_e2e = max(1, args.steps)
         run_e2e(n_e2e)
@@ -636,7 +649,12 @@ def main():
         dt = float(tt.item())
         e2e = {"value": n_halos_total / dt, "unit": "halos/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt,
-               "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i", "numa_node": numa}
+               "pipeline": "ChunkFeed: upload of chunk i+1 overlaps processing of chunk i", "numa_node": numa,
+               "h2d_copy_alone_ms": round(1e3 * copy_alone, 2),
+               "h2d_copy_alone_gbs_per_gpu": round(h2d / copy_alone / 1e9, 2),
+               "note": "host arrays are pinned once, outside the timed region, like SharedArray buffers registered with "
+                       "cudaHostRegister at allocation would be; the step is bound by the PCIe copy whenever "
+                       "h2d_copy_alone_ms exceeds the device-resident ms_per_step"}
 
     # -------------------------------------------------------- roofline (rank 0)
     # per kernel: launches and device time from the CUDA events the library records around every launch of the
