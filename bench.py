@@ -695,11 +695,15 @@ def main():
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")))
-        traffic = tr.get(args.workload, {}).get(dom)
+        per_step = tr.get(args.workload, {}).get(dom)
+        if per_step is not None:  # the table holds the sum over one step's launches
+            traffic = round(per_step / max(modelled[dom]["launches_per_step"], 1.0))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": modelled[dom]["achieved_gbs"], "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": modelled[dom]["frac"], "traffic": traffic,
+                "alg_bytes_per_launch": round(modelled[dom]["alg_bytes_per_unit"] * modelled[dom]["units_per_step"] /
+                                              max(modelled[dom]["launches_per_step"], 1.0)),
                 "launches_per_step": modelled[dom]["launches_per_step"], "ms_per_step": modelled[dom]["ms"],
                 "share_of_step": round(modelled[dom]["ms"] / ms_step, 3)}
     total_alg = 32.0 * n_part + 48.0 * pairs + 8.0 * H * ncol

@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(NT) k_sort_bucket(const Bucket* __restrict__ b
 // One CTA (CS == 1) or one cluster of CS CTAs (halos above SCAN_BIG records)
 // per halo of the list; the per-halo work is scan_solve_halo (scan.cuh).
 template <int NCH, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ? 2 : 1)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ? (CS == 1 ? 3 : 2) : 1)
     k_scan_solve(HaloArrays ha, DevCfg cfg, const uint32_t* __restrict__ try_list,
                  const unsigned int* __restrict__ n_try, const Rec* __restrict__ recs,
                  uint32_t* __restrict__ next, Counters* ctr,
@@ -944,7 +944,7 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
             add(p + "DtoTgas", 1); add(p + "DtoTstar", 1);
             add(p + "StellarRotationalVelocity", 1); add(p + "StellarCylindricalVelocityDispersion", 1);
             add(p + "StellarCylindricalVelocityDispersionVertical", 1);
-            add(p + "StellarCylindricalVelocityDispersionDiscPlane", 1); add(p + "kappa_scratch", 2);
+            add(p + "StellarCylindricalVelocityDispersionDiscPlane", 1);
         }
         if (cfg->property_flags & PF_TENS) {
             add(p + (kind == 2 ? "StellarInertiaTensorNoniterative" : "TotalInertiaTensorNoniterative"), 6);
@@ -1048,6 +1048,13 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     WS_GET(bank_off, unsigned long long, h, "h_bank_off", H); ha.bank_off = bank_off;
     WS_GET(cuts_arr, Cuts, h, "h_cuts", H); ha.cuts = cuts_arr;
     ha.gbank = nullptr;
+    ha.kraw_nb = (dc.do_sub ? 1 : 0) + dc.n_so + dc.n_ap;
+    ha.kraw = nullptr;
+    if (dc.flags & PF_KAPPA) {
+        WS_GET(kraw, double, h, "h_kraw", (size_t)H * ha.kraw_nb * 2 + 2);
+        ha.kraw = kraw;
+        CUDA_TRY(cudaMemsetAsync(kraw, 0, sizeof(double) * (size_t)H * ha.kraw_nb * 2, stream));
+    }
     const int bank_stride = soap_bank_stride(dc);
     WS_GET(ctr, Counters, h, "h_ctr", 8);  // [0] current round, [2..4] the fused tiers
     WS_GET(n_pend_dev, unsigned int, h, "h_npend", 4);
@@ -1091,41 +1098,61 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         LAUNCH(h, k_tier_scan, 1, TIER_BUCKETS, 0, stream, size_hist, tier_n, tl);
         LAUNCH(h, k_tier_place, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, list0, list1, list2,
                size_hist + TIER_BUCKETS, size_hist, tl);
-        Counters* tctr = ctr + 2;
-        uint32_t* round_next[2] = {listB, big_list};  // free until the general path starts
-        for (int t = 0; t < NTIER; t++) {
-            // overflow goes to the next tier, from the last one to the general path's pending list
-            uint32_t* ovf = t + 1 < NTIER ? tier_list[t + 1] : pend;
-            unsigned int* n_ovf = t + 1 < NTIER ? tier_n + t + 1 : tier_n + 3;
-            unsigned int n_host = 0;
-            CUDA_TRY(cudaMemcpyAsync(&n_host, tier_n + t, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            const uint32_t* list = tier_list[t];
-            const unsigned int* n_dev = tier_n + t;
-            for (int round = 0; n_host > 0; round++) {
-                if (round > 200) SOAP_FAIL("soap_process_halos: radius ladder did not terminate");
-                CUDA_TRY(cudaMemsetAsync(tctr, 0, sizeof(Counters), stream));
-                CUDA_TRY(cudaMemsetAsync(tier_n + 8, 0, sizeof(unsigned int), stream));
-                log.begin(t == 0 ? "tier_0" : "tier_1", stream);
-                // stragglers that still ask for a larger radius after TIER_ROUNDS rounds move on like overflow:
-                // a handful of halos climbing the ladder one launch sequence per rung is what the general
-                // path's 12-rung look-ahead is for
-                const bool last = round + 1 >= TIER_ROUNDS;
-                if (soap_tier_round(c, dc, ha, t, list, n_dev, n_host, ovf, n_ovf, tier_n + 8, try_list,
-                                    last ? ovf : round_next[round & 1], last ? n_ovf : &tctr->n_next, tctr, item_minr,
-                                    item_minfof, stream) < 0)
+        // The two tiers keep their own lists, scratch and counters and run their rounds side by side (tier 1 on a
+        // side stream): each tier's solve is a thread-per-halo kernel whose tail leaves most of the GPU idle, the
+        // other tier's sweeps fill it.  A halo that outgrows tier 0 joins tier 1's next round; in the last round
+        // overflow and stragglers (halos still asking for a larger radius: a handful climbing the ladder one launch
+        // sequence per rung is what the general path's 12-rung look-ahead is for) move on like overflow.
+        if (h->side_init()) SOAP_FAIL("soap_process_halos: cannot create side streams");
+        WS_GET(t1_minr, unsigned long long, h, "h_t1_minr", H);
+        WS_GET(t1_minfof, int32_t, h, "h_t1_minfof", H);
+        Counters* tctr[NTIER] = {ctr + 2, ctr + 3};
+        uint32_t* round_next[NTIER][2] = {{listB, big_list}, {multi_list, huge_list}};  // free until the general path starts
+        uint32_t* tier_try[NTIER] = {try_list, acc_list};
+        unsigned long long* tier_minr[NTIER] = {item_minr, t1_minr};
+        int32_t* tier_minfof[NTIER] = {item_minfof, t1_minfof};
+        cudaStream_t tier_stream[NTIER] = {stream, h->side[0]};
+        const uint32_t* list[NTIER] = {tier_list[0], tier_list[1]};
+        const unsigned int* n_dev[NTIER] = {tier_n + 0, tier_n + 1};
+        unsigned int n_host[NTIER] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(n_host, tier_n, NTIER * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int round = 0; n_host[0] + n_host[1] > 0; round++) {
+            if (round > TIER_ROUNDS) SOAP_FAIL("soap_process_halos: tier rounds did not terminate");
+            // both tiers' counters are cleared before either tier starts: tier 0 appends its overflow to tier 1's
+            // next list while tier 1 is running
+            CUDA_TRY(cudaMemsetAsync(tctr[0], 0, NTIER * sizeof(Counters), stream));
+            CUDA_TRY(cudaMemsetAsync(tier_n + 8, 0, NTIER * sizeof(unsigned int), stream));
+            CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
+            CUDA_TRY(cudaStreamWaitEvent(tier_stream[1], h->ev_fork, 0));
+            for (int t = 0; t < NTIER; t++) {
+                if (n_host[t] == 0) continue;
+                // tier 0 runs TIER_ROUNDS rounds, tier 1 one more (for what tier 0 hands over in its last one)
+                const bool last = round + 1 >= TIER_ROUNDS + t;
+                const bool to_general = t + 1 >= NTIER;
+                uint32_t* ovf = to_general ? pend : round_next[t + 1][round & 1];
+                unsigned int* n_ovf = to_general ? tier_n + 3 : &tctr[t + 1]->n_next;
+                log.begin(t == 0 ? "tier_0" : "tier_1", tier_stream[t]);
+                if (soap_tier_round(c, dc, ha, t, list[t], n_dev[t], n_host[t], ovf, n_ovf, tier_n + 8 + t, tier_try[t],
+                                    last ? ovf : round_next[t][round & 1], last ? n_ovf : &tctr[t]->n_next, tctr[t],
+                                    tier_minr[t], tier_minfof[t], tier_stream[t]) < 0)
                     return -1;
-                log.end(stream);
-                Counters tc;
-                CUDA_TRY(cudaMemcpyAsync(tier_n + 12, &tctr->n_next, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
-                CUDA_TRY(cudaMemcpyAsync(&tc, tctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                CUDA_TRY(cudaStreamSynchronize(stream));
-                total_pairs += tc.pairs;
-                total_cand += tc.candidates;
-                c->last_tier_pairs[t] += (int64_t)tc.pairs;
-                list = round_next[round & 1];
-                n_dev = tier_n + 12;
-                n_host = tc.n_next;
+                log.end(tier_stream[t]);
+            }
+            CUDA_TRY(cudaEventRecord(h->ev_join[0], tier_stream[1]));
+            CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[0], 0));
+            Counters tc[NTIER];
+            for (int t = 0; t < NTIER; t++)
+                CUDA_TRY(cudaMemcpyAsync(tier_n + 12 + t, &tctr[t]->n_next, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(tc, tctr[0], NTIER * sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (int t = 0; t < NTIER; t++) {
+                total_pairs += tc[t].pairs;
+                total_cand += tc[t].candidates;
+                c->last_tier_pairs[t] += (int64_t)tc[t].pairs;
+                list[t] = round_next[t][round & 1];
+                n_dev[t] = tier_n + 12 + t;
+                n_host[t] = round + 1 >= TIER_ROUNDS + t ? 0 : tc[t].n_next;
             }
         }
     }

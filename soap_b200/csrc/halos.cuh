@@ -47,7 +47,7 @@ __host__ __device__ inline BlockLayout block_layout(uint32_t flags, int n_extra)
     b.kin = (flags & PF_KIN) ? o : -1;
     if (flags & PF_KIN) o += 51;
     b.kappa = (flags & PF_KAPPA) ? o : -1;
-    if (flags & PF_KAPPA) o += 11;  // kappa x3, DtoT x2, stellar rotation + cylindrical dispersions x4, 2 scratch
+    if (flags & PF_KAPPA) o += 9;  // kappa x3, DtoT x2, stellar rotation + cylindrical dispersions x4
     b.tens = (flags & PF_TENS) ? o : -1;
     if (flags & PF_TENS) o += (flags & PF_ITER) ? 24 : 12;  // non-iterative pair, then the iterative pair
     b.hmr = (flags & PF_HMR) ? o : -1;
@@ -155,6 +155,8 @@ struct HaloArrays {
     int32_t* mslot;            // global bank slot of multi-item halos, -1 otherwise (projected apertures)
     // moment banks of every halo accepted this round (written by the moment kernels, read by k_rows)
     double* gbank;
+    double* kraw;  // [H][kraw_nb][2] raw sums of the stellar cylindrical dispersions that have no row column
+    int kraw_nb;   // selection blocks per halo: BoundSubhalo + SO variations + apertures
     unsigned long long* bank_off;  // [H] offset of the halo's banks in gbank (doubles)
     Cuts* cuts;                    // [H] shell cuts of the selections committed this round
     // ladder look-ahead: one count sweep bins the sphere of the furthest rung by rung

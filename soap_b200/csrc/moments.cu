@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, Dev
         __syncthreads();
         for (int i = threadIdx.x; i < ns * 11; i += TB) {
             const double a = acc[i / 11][i % 11];
-            if (a != 0.0) atomicAdd(&sel[i / 11].out[i % 11], a);
+            if (a != 0.0) atomicAdd(sel[i / 11].slot(i % 11), a);
         }
         __syncthreads();
     }

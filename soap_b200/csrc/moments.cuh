@@ -434,11 +434,13 @@ struct KapSel {
     int cyl_ok;           // Nstar >= 2 and sum(Lstar) != 0 (aperture_properties.py:1483-1490)
     double R;
     int incl, is_sub, strict;  // strict: r < R (SO selections, SO_properties.py:485) instead of r <= R
-    double* out;  // the block's 11 kappa / rotation slots
+    double* out;   // the block's 9 kappa / rotation columns, holding raw sums 0..8 until kappa_finish_row
+    double* out2;  // raw sums 9, 10 (sum m v_phi^2, sum m v_z^2) in HaloArrays::kraw
+    __device__ double* slot(int j) const { return j < 9 ? out + j : out2 + (j - 9); }
 };
 constexpr int KAPPA_MAX_SEL = 1 + SOAP_MAX_SO + SOAP_MAX_APERTURES;
 
-__device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl) {
+__device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl, double* raw2) {
     const double* kin = blk + bl.kin;
     const double Mg = blk[4], Ms = blk[6];
     for (int g = 0; g < 3; g++) {
@@ -457,6 +459,7 @@ __device__ inline void kappa_refs(KapSel& k, double* blk, const BlockLayout& bl)
         for (int d = 0; d < 3; d++) k.lh[g][d] = nrm > 0.0 ? L[d] / nrm : 0.0;
     }
     k.out = blk + bl.kappa;
+    k.out2 = raw2;
     // stellar frame: z = L_star / |L_star|, x = helper x z normalised, y = z x x
     {
         const double* o = kin + 30;
@@ -482,9 +485,10 @@ __device__ inline int kappa_build_sels(KapSel* sel, const DevCfg& cfg, const Hal
                                        int c_hi) {
     const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
     double* row = ha.out + (int64_t)h * ha.ncol;
+    double* raw2 = ha.kraw + (int64_t)h * ha.kraw_nb * 2;  // two doubles per (halo, selection block)
     int n = 0;
     if (cfg.do_sub && c_lo == 0) {
-        kappa_refs(sel[n], row + cfg.lay.sub, cfg.lay.bsub);
+        kappa_refs(sel[n], row + cfg.lay.sub, cfg.lay.bsub, raw2);
         sel[n].is_sub = 1; sel[n].incl = 0; sel[n].R = 0.0; sel[n].strict = 0;
         n++;
     }
@@ -494,14 +498,14 @@ __device__ inline int kappa_build_sels(KapSel* sel, const DevCfg& cfg, const Hal
         const ScanRes* sr = ha.sres + h;
         for (int q = 0; q < cfg.n_so; q++)
             if (off_so + q >= c_lo && off_so + q < c_hi && sr->so_exists[q]) {
-                kappa_refs(sel[n], row + cfg.lay.so[q], cfg.lay.bso);
+                kappa_refs(sel[n], row + cfg.lay.so[q], cfg.lay.bso, raw2 + 2 * (off_so + q));
                 sel[n].is_sub = 0; sel[n].incl = 1; sel[n].R = sr->so_r[q]; sel[n].strict = 1;
                 n++;
             }
     }
     for (int a = 0; a < cfg.n_ap; a++)
         if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) {
-            kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap);
+            kappa_refs(sel[n], row + cfg.lay.ap[a], cfg.lay.bap, raw2 + 2 * (off_ap + a));
             sel[n].is_sub = 0; sel[n].incl = cfg.ap_incl[a]; sel[n].R = cfg.ap_r[a]; sel[n].strict = 0;
             n++;
         }
@@ -551,9 +555,11 @@ __device__ __forceinline__ void kappa_add(const KapSel* sel, int ns, double (*ac
 __device__ inline void kappa_finish_row(const DevCfg& cfg, const HaloArrays& ha, uint32_t h, int c_lo, int c_hi) {
     const int off_ap = (cfg.do_sub ? 1 : 0) + cfg.n_so;
     double* row = ha.out + (int64_t)h * ha.ncol;
-    auto fin = [&](double* blk, const BlockLayout& bl) {
+    const double* raw2 = ha.kraw + (int64_t)h * ha.kraw_nb * 2;
+    auto fin = [&](double* blk, const BlockLayout& bl, int c) {
         const double* kin = blk + bl.kin;
         double* o = blk + bl.kappa;
+        const double o9 = raw2[2 * c], o10 = raw2[2 * c + 1];
         const double Mg = blk[4], Ms = blk[6];
         const double* gk = kin;        // gas: com 3, vcom 3, L 3, veldisp 6
         const double* sk = kin + 30;   // stars
@@ -579,25 +585,24 @@ __device__ inline void kappa_finish_row(const DevCfg& cfg, const HaloArrays& ha,
         // aperture_properties.py:1502-1536): mean v_phi, sqrt(sum sigma^2 / 3), sigma_z, sqrt(sigma_r^2 + sigma_phi^2)
         {
             double mean[3], var[3];
-            const bool have = Ms != 0.0 && (o[5] != 0.0 || o[6] != 0.0 || o[7] != 0.0 || o[8] != 0.0 || o[9] != 0.0 || o[10] != 0.0);
+            const bool have = Ms != 0.0 && (o[5] != 0.0 || o[6] != 0.0 || o[7] != 0.0 || o[8] != 0.0 || o9 != 0.0 || o10 != 0.0);
             for (int c = 0; c < 3; c++) {
                 mean[c] = have ? o[5 + c] / Ms : 0.0;
-                var[c] = have ? fmax(o[8 + c] / Ms - mean[c] * mean[c], 0.0) : 0.0;
+                const double s2 = c == 0 ? o[8] : c == 1 ? o9 : o10;
+                var[c] = have ? fmax(s2 / Ms - mean[c] * mean[c], 0.0) : 0.0;
             }
             o[5] = mean[1];
             o[6] = sqrt((var[0] + var[1] + var[2]) / 3.0);
             o[7] = sqrt(var[2]);
             o[8] = sqrt(var[0] + var[1]);
-            o[9] = 0.0;
-            o[10] = 0.0;
         }
     };
-    if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub);
+    if (cfg.do_sub && c_lo == 0) fin(row + cfg.lay.sub, cfg.lay.bsub, 0);
     for (int q = 0; q < cfg.n_so; q++)
         if ((cfg.do_sub ? 1 : 0) + q >= c_lo && (cfg.do_sub ? 1 : 0) + q < c_hi && ha.sres[h].so_exists[q])
-            fin(row + cfg.lay.so[q], cfg.lay.bso);
+            fin(row + cfg.lay.so[q], cfg.lay.bso, (cfg.do_sub ? 1 : 0) + q);
     for (int a = 0; a < cfg.n_ap; a++)
-        if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) fin(row + cfg.lay.ap[a], cfg.lay.bap);
+        if (off_ap + a >= c_lo && off_ap + a < c_hi && ((ha.sres[h].ap_on >> a) & 1u)) fin(row + cfg.lay.ap[a], cfg.lay.bap, off_ap + a);
 }
 
 #endif  // __CUDACC__

@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(32 * NW) k_tier_kappa(ChunkView v, HaloArrays 
         __syncwarp();
         for (int i = lane; i < ns * 11; i += 32) {
             const double a = kacc[i / 11][i % 11];
-            if (a != 0.0) ksel[i / 11].out[i % 11] += a;
+            if (a != 0.0) *ksel[i / 11].slot(i % 11) += a;
         }
         __syncwarp();
     }
@@ -636,9 +636,11 @@ int soap_tier_round(soap_chunk* c, const DevCfg& cfg, HaloArrays& ha, int tier, 
     // sphere's stellar tensors count every star loaded (aperture_properties.py:3579-3594), the iterative tensors
     // use the sphere of the rung that committed them
     const int multi = (cfg.n_ap == 0 && cfg.n_pj == 0 && !(cfg.flags & PF_ITER)) ? 1 : 0;
-    Rec* recs = (Rec*)h->get("h_trecs", sizeof(Rec) * (size_t)n_upper * cap);
-    uint32_t* pids = (uint32_t*)h->get("h_tpids", sizeof(uint32_t) * (size_t)n_upper * cap);
-    ha.gbank = (double*)h->get("h_gbank", sizeof(double) * (size_t)bank_stride * ((size_t)n_upper + 1));
+    // scratch per tier: the two tiers run concurrently (halos.cu)
+    const char* nm[2][3] = {{"h_trecs0", "h_tpids0", "h_tbank0"}, {"h_trecs1", "h_tpids1", "h_tbank1"}};
+    Rec* recs = (Rec*)h->get(nm[tier != 0][0], sizeof(Rec) * (size_t)n_upper * cap);
+    uint32_t* pids = (uint32_t*)h->get(nm[tier != 0][1], sizeof(uint32_t) * (size_t)n_upper * cap);
+    ha.gbank = (double*)h->get(nm[tier != 0][2], sizeof(double) * (size_t)bank_stride * ((size_t)n_upper + 1));
     if (!recs || !pids || !ha.gbank) return -1;
 #define FRONT(NCH, CAP, NW)                                                                                            \
     launch_front<NCH, CAP, NW>(c, cfg, ha, list, n_list, n_upper, overflow, n_overflow, queue_cursor, try_list, ctr, recs, \

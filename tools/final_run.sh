@@ -10,5 +10,5 @@ done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_reference.json
 cut -c1-300 gpurun_out/r02_bench_reference.json
 bash tools/launches.sh r02_config2 > /dev/null 2>&1
-bash tools/ncu_kernels.sh r02_config2 "k_" 60 > /dev/null 2>&1
+bash tools/ncu_kernels.sh r02_config2 "k_" 150 > /dev/null 2>&1
 tail -3 gpurun_out/ncu_r02_config2.txt
