@@ -98,6 +98,34 @@ struct soap_handle {
         }
         return cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess ? 0 : -1;
     }
+    // the small-halo tiers run on their own two streams, concurrently with the general path's first round
+    static constexpr int TIER_EV = 8;
+    cudaStream_t tstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_tfork = nullptr, ev_tjoin[2] = {nullptr, nullptr}, ev_tround[TIER_EV] = {};
+    int tier_init() {
+        if (tstream[0]) return 0;
+        for (int i = 0; i < 2; i++) {
+            if (cudaStreamCreateWithFlags(&tstream[i], cudaStreamNonBlocking) != cudaSuccess) return -1;
+            if (cudaEventCreateWithFlags(&ev_tjoin[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+        }
+        for (int i = 0; i < TIER_EV; i++)
+            if (cudaEventCreateWithFlags(&ev_tround[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+        return cudaEventCreateWithFlags(&ev_tfork, cudaEventDisableTiming) == cudaSuccess ? 0 : -1;
+    }
+    void streams_destroy() {
+        for (int i = 0; i < 3; i++) {
+            if (side[i]) cudaStreamDestroy(side[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (int i = 0; i < 2; i++) {
+            if (tstream[i]) cudaStreamDestroy(tstream[i]);
+            if (ev_tjoin[i]) cudaEventDestroy(ev_tjoin[i]);
+        }
+        for (int i = 0; i < TIER_EV; i++)
+            if (ev_tround[i]) cudaEventDestroy(ev_tround[i]);
+        if (ev_tfork) cudaEventDestroy(ev_tfork);
+    }
     std::map<std::string, WsBuf> ws;
     // returns nullptr on failure (error string set)
     void* get(const char* name, size_t bytes) {

@@ -64,7 +64,7 @@ constexpr int SCAN_CS_HUGE = 16;
 // halos with up to this many bound particles start in tier 0 / 1 of the staged small-halo path (tier.cu:
 // spheres of up to 256 / 1024 particles); larger ones take the general path
 constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 500;
-constexpr int TIER_ROUNDS = 3;
+constexpr int TIER_ROUNDS = 5;
 
 struct Bucket {
     unsigned long long start;
@@ -159,8 +159,10 @@ __global__ void __launch_bounds__(PLAN_NT) k_plan_items(ChunkView v, HaloArrays 
     // replan: the sweep of the accepted rung (collect / moments)
     double r = ha.cur_r[h];
     if (!replan) {
+        // a halo that has not failed a rung yet looks 4 rungs ahead even when the round's stragglers look further:
+        // the sphere of the 12th rung holds ~700 times the volume
         double rr[LOOK_MAX];
-        const int nr = ladder_radii(r, ha.rr_in[h], look, rr);
+        const int nr = ladder_radii(r, ha.rr_in[h], (look > 4 && ha.nloop[h] == 0) ? 4 : look, rr);
         r = rr[nr - 1];
         if (lane == 0) ha.look[h] = nr;
         if (lane < LOOK_MAX) { ha.rung_cnt[(size_t)h * LOOK_MAX + lane] = 0; ha.rung_msum[(size_t)h * LOOK_MAX + lane] = 0.0; }
@@ -1073,7 +1075,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     c->last_rounds = 0;
     uint32_t* pend = listA;
     uint32_t* next = listB;
-    // tiers: the staged small-halo path first (tier.cu), the rest and its overflow below
+    // tiers: the staged small-halo path (tier.cu) next to the rest; its overflow joins below
     constexpr int NTIER = 2;
     const long long tier_nexp[NTIER] = {SMALL_NEXP_0, SMALL_NEXP_1};
     uint32_t* tier_list[3 + 1];
@@ -1094,73 +1096,123 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     LAUNCH(h, k_init, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, pend, tier_n, size_hist, tl);
     unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
     for (int t = 0; t < 3; t++) c->last_tier_pairs[t] = 0;
+    bool tiers_running = false;
+    unsigned int n_pend_first = 0;
     if (tiers_on) {
         LAUNCH(h, k_tier_scan, 1, TIER_BUCKETS, 0, stream, size_hist, tier_n, tl);
         LAUNCH(h, k_tier_place, grid_for(H, 128), 128, 0, stream, ha, (int64_t)H, list0, list1, list2,
                size_hist + TIER_BUCKETS, size_hist, tl);
-        // The two tiers keep their own lists, scratch and counters and run their rounds side by side (tier 1 on a
-        // side stream): each tier's solve is a thread-per-halo kernel whose tail leaves most of the GPU idle, the
-        // other tier's sweeps fill it.  A halo that outgrows tier 0 joins tier 1's next round; in the last round
-        // overflow and stragglers (halos still asking for a larger radius: a handful climbing the ladder one launch
-        // sequence per rung is what the general path's 12-rung look-ahead is for) move on like overflow.
-        if (h->side_init()) SOAP_FAIL("soap_process_halos: cannot create side streams");
-        WS_GET(t1_minr, unsigned long long, h, "h_t1_minr", H);
-        WS_GET(t1_minfof, int32_t, h, "h_t1_minfof", H);
-        Counters* tctr[NTIER] = {ctr + 2, ctr + 3};
-        uint32_t* round_next[NTIER][2] = {{listB, big_list}, {multi_list, huge_list}};  // free until the general path starts
-        uint32_t* tier_try[NTIER] = {try_list, acc_list};
-        unsigned long long* tier_minr[NTIER] = {item_minr, t1_minr};
-        int32_t* tier_minfof[NTIER] = {item_minfof, t1_minfof};
-        cudaStream_t tier_stream[NTIER] = {stream, h->side[0]};
-        const uint32_t* list[NTIER] = {tier_list[0], tier_list[1]};
-        const unsigned int* n_dev[NTIER] = {tier_n + 0, tier_n + 1};
-        unsigned int n_host[NTIER] = {0, 0};
-        CUDA_TRY(cudaMemcpyAsync(n_host, tier_n, NTIER * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        for (int round = 0; n_host[0] + n_host[1] > 0; round++) {
-            if (round > TIER_ROUNDS) SOAP_FAIL("soap_process_halos: tier rounds did not terminate");
-            // both tiers' counters are cleared before either tier starts: tier 0 appends its overflow to tier 1's
-            // next list while tier 1 is running
-            CUDA_TRY(cudaMemsetAsync(tctr[0], 0, NTIER * sizeof(Counters), stream));
-            CUDA_TRY(cudaMemsetAsync(tier_n + 8, 0, NTIER * sizeof(unsigned int), stream));
-            CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
-            CUDA_TRY(cudaStreamWaitEvent(tier_stream[1], h->ev_fork, 0));
+        // The tiers run asynchronously: all rounds of both tiers are enqueued up front on two streams of their own
+        // (list sizes stay on the device, grids are sized for upper bounds), while the general path's first round
+        // runs on the caller's stream over the halos that were too large for the tiers from the start.  Each
+        // tier's solve is a thread-per-halo kernel whose tail leaves most of the GPU idle; the other tier's and the
+        // general path's sweeps fill it.  A halo that outgrows tier 0 joins tier 1's next round (tier 1 waits for the
+        // event that closes tier 0's round).  In a tier's last round overflow and stragglers (halos still asking for
+        // a larger radius) go to `late`, which joins the general path's pending list after its first round.
+        if (h->tier_init()) SOAP_FAIL("soap_process_halos: cannot create the tier streams");
+        static_assert(TIER_ROUNDS + 1 <= soap_handle::TIER_EV, "one event per tier round");
+        constexpr int NR = TIER_ROUNDS + 1;  // tier 0 runs TIER_ROUNDS rounds, tier 1 one more
+        WS_GET(tctr_all, Counters, h, "h_tctr", NTIER * NR);
+        WS_GET(tcur, unsigned int, h, "h_tcur", NTIER * NR);
+        CUDA_TRY(cudaMemsetAsync(tctr_all, 0, NTIER * NR * sizeof(Counters), stream));
+        CUDA_TRY(cudaMemsetAsync(tcur, 0, NTIER * NR * sizeof(unsigned int), stream));
+        // one output list per (tier, round): tier 0 runs ahead of tier 1 and appends to tier 1's lists of later rounds
+        // while tier 1 still reads its earlier ones
+        uint32_t* t_next[NTIER][NR];
+        uint32_t* t_try[NTIER];
+        unsigned long long* t_minr[NTIER];
+        int32_t* t_minfof[NTIER];
+        {
+            const char* nm[NTIER][4] = {{"h_t0_next", "h_t0_try", "h_t0_minr", "h_t0_minfof"},
+                                        {"h_t1_next", "h_t1_try", "h_t1_minr", "h_t1_minfof"}};
             for (int t = 0; t < NTIER; t++) {
-                if (n_host[t] == 0) continue;
-                // tier 0 runs TIER_ROUNDS rounds, tier 1 one more (for what tier 0 hands over in its last one)
-                const bool last = round + 1 >= TIER_ROUNDS + t;
-                const bool to_general = t + 1 >= NTIER;
-                uint32_t* ovf = to_general ? pend : round_next[t + 1][round & 1];
-                unsigned int* n_ovf = to_general ? tier_n + 3 : &tctr[t + 1]->n_next;
-                log.begin(t == 0 ? "tier_0" : "tier_1", tier_stream[t]);
-                if (soap_tier_round(c, dc, ha, t, list[t], n_dev[t], n_host[t], ovf, n_ovf, tier_n + 8 + t, tier_try[t],
-                                    last ? ovf : round_next[t][round & 1], last ? n_ovf : &tctr[t]->n_next, tctr[t],
-                                    tier_minr[t], tier_minfof[t], tier_stream[t]) < 0)
-                    return -1;
-                log.end(tier_stream[t]);
-            }
-            CUDA_TRY(cudaEventRecord(h->ev_join[0], tier_stream[1]));
-            CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[0], 0));
-            Counters tc[NTIER];
-            for (int t = 0; t < NTIER; t++)
-                CUDA_TRY(cudaMemcpyAsync(tier_n + 12 + t, &tctr[t]->n_next, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
-            CUDA_TRY(cudaMemcpyAsync(tc, tctr[0], NTIER * sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            for (int t = 0; t < NTIER; t++) {
-                total_pairs += tc[t].pairs;
-                total_cand += tc[t].candidates;
-                c->last_tier_pairs[t] += (int64_t)tc[t].pairs;
-                list[t] = round_next[t][round & 1];
-                n_dev[t] = tier_n + 12 + t;
-                n_host[t] = round + 1 >= TIER_ROUNDS + t ? 0 : tc[t].n_next;
+                uint32_t* lists = (uint32_t*)h->get(nm[t][0], sizeof(uint32_t) * (size_t)H * NR);
+                t_try[t] = (uint32_t*)h->get(nm[t][1], sizeof(uint32_t) * (size_t)H);
+                t_minr[t] = (unsigned long long*)h->get(nm[t][2], sizeof(unsigned long long) * (size_t)H);
+                t_minfof[t] = (int32_t*)h->get(nm[t][3], sizeof(int32_t) * (size_t)H);
+                if (!lists || !t_try[t] || !t_minr[t] || !t_minfof[t]) return -1;
+                for (int r = 0; r < NR; r++) t_next[t][r] = lists + (size_t)H * r;
             }
         }
+        uint32_t* late = list2;  // counted in tier_n[4]
+        unsigned int n0[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpyAsync(n0, tier_n, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        // upper bounds of the list sizes: tier 0's lists only shrink; tier 1 also receives what tier 0 hands over,
+        // provisioned for an eighth of tier 0 (a longer list sends its surplus on to the general path)
+        unsigned int extra = n0[0] / 8 > 4096u ? n0[0] / 8 : 4096u;
+        if (extra > n0[0]) extra = n0[0];
+        const unsigned int n_up[NTIER] = {n0[0], n0[1] + extra};
+        if (n_up[0] + n_up[1] > 0) {
+            CUDA_TRY(cudaEventRecord(h->ev_tfork, stream));
+            for (int t = 0; t < NTIER; t++) {
+                cudaStream_t ts = h->tstream[t];
+                CUDA_TRY(cudaStreamWaitEvent(ts, h->ev_tfork, 0));
+                if (n_up[t] == 0) continue;
+                const int rounds = TIER_ROUNDS + t;
+                log.begin(t == 0 ? "tier_0" : "tier_1", ts);
+                for (int round = 0; round < rounds; round++) {
+                    Counters* tc = tctr_all + t * NR + round;
+                    const bool last = round + 1 >= rounds;
+                    const bool to_general = last || t + 1 >= NTIER;
+                    // tier 0, round r -> tier 1's list of round r + 1 (the list tier 1's round r also appends to)
+                    uint32_t* ovf = to_general ? late : t_next[t + 1][round];
+                    unsigned int* n_ovf = to_general ? tier_n + 4 : &tctr_all[(t + 1) * NR + round].n_next;
+                    const uint32_t* list = round == 0 ? tier_list[t] : t_next[t][round - 1];
+                    const unsigned int* n_dev = round == 0 ? tier_n + t : &tctr_all[t * NR + round - 1].n_next;
+                    if (t == 1 && round >= 1 && n_up[0] > 0 && round - 1 < TIER_ROUNDS)
+                        CUDA_TRY(cudaStreamWaitEvent(ts, h->ev_tround[round - 1], 0));
+                    if (soap_tier_round(c, dc, ha, t, list, n_dev, n_up[t], ovf, n_ovf, tcur + t * NR + round, t_try[t],
+                                        last ? late : t_next[t][round], last ? tier_n + 4 : &tc->n_next, tc,
+                                        t_minr[t], t_minfof[t], ts) < 0)
+                        return -1;
+                    if (t == 0) CUDA_TRY(cudaEventRecord(h->ev_tround[round], ts));
+                }
+                log.end(ts);
+                CUDA_TRY(cudaEventRecord(h->ev_tjoin[t], ts));
+            }
+            tiers_running = true;
+        }
+        n_pend_first = n0[3];
     }
+    // wait for the tiers, add up their counters; returns the number of halos in `late` (list2)
+    auto join_tiers = [&](unsigned int* n_late) -> int {
+        *n_late = 0;
+        if (!tiers_running) return 0;
+        tiers_running = false;
+        constexpr int NR = TIER_ROUNDS + 1;
+        Counters* tctr_all = (Counters*)h->get("h_tctr", NTIER * NR * sizeof(Counters));
+        if (!tctr_all) return -1;
+        for (int t = 0; t < NTIER; t++) CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_tjoin[t], 0));
+        Counters tc[NTIER * NR];
+        CUDA_TRY(cudaMemcpyAsync(tc, tctr_all, sizeof(tc), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(n_late, tier_n + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int t = 0; t < NTIER; t++)
+            for (int r = 0; r < NR; r++) {
+                total_pairs += tc[t * NR + r].pairs;
+                total_cand += tc[t * NR + r].candidates;
+                c->last_tier_pairs[t] += (int64_t)tc[t * NR + r].pairs;
+                c->last_small_pairs += (int64_t)tc[t * NR + r].pairs;
+            }
+        return 0;
+    };
     unsigned int n_pend = 0;
-    CUDA_TRY(cudaMemcpyAsync(n_pend_dev, tier_n + 3, sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(&n_pend, tier_n + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    if (tiers_on) {
+        n_pend = n_pend_first;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(&n_pend, tier_n + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    c->last_small_pairs = 0;
+    if (n_pend == 0) {  // nothing but small halos: what the tiers hand over is the pending list
+        unsigned int n_late = 0;
+        if (join_tiers(&n_late)) return -1;
+        if (n_late > 0) CUDA_TRY(cudaMemcpyAsync(pend, list2, n_late * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+        n_pend = n_late;
+    }
+    CUDA_TRY(cudaMemcpyAsync(n_pend_dev, &n_pend, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    c->last_small_pairs = (int64_t)total_pairs;
     const int sm = h->sm_count;
     // per device, so set on every call (cheap)
     CUDA_TRY(cudaFuncSetAttribute(k_sort_bucket<SB_CAP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1379,6 +1431,16 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         total_pairs += hc2.pairs;
         total_mom_pairs += hc2.mom_pairs;
         n_pend = hc2.n_next;
+        if (tiers_running) {  // what the tiers hand over joins the second round
+            unsigned int n_late = 0;
+            if (join_tiers(&n_late)) return -1;
+            if (n_late > 0) {
+                CUDA_TRY(cudaMemcpyAsync(next + n_pend, list2, n_late * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+                n_pend += n_late;
+                CUDA_TRY(cudaMemcpyAsync(n_pend_dev, &n_pend, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+        }
         uint32_t* t = pend; pend = next; next = t;
     }
     if (dc.flags & PF_ITER) {

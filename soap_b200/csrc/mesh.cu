@@ -266,11 +266,7 @@ int soap_destroy(soap_handle* h) {
     cudaSetDevice(h->device);
     for (auto& kv : h->ws)
         if (kv.second.p) cudaFree(kv.second.p);
-    for (int i = 0; i < 3; i++) {
-        if (h->side[i]) cudaStreamDestroy(h->side[i]);
-        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-    }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    h->streams_destroy();
     delete h;
     return 0;
 }

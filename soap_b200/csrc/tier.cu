@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
                                                         Rec* __restrict__ recs, uint32_t* __restrict__ pids,
                                                         unsigned long long* __restrict__ item_minr,
                                                         int32_t* __restrict__ item_minfof, int bank_stride, int multi,
-                                                        unsigned long long rec_capacity) {
+                                                        unsigned int slot_cap, unsigned long long rec_capacity) {
     constexpr uint32_t CAND_MAX = 16u * CAP;  // larger sweeps belong to the CTA-wide kernels of the general path
     constexpr int U = 4;                      // candidate groups in flight per warp (memory-level parallelism)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(32 * NW, CAP <= 256 ? 3 : 1) k_tier_front(Chun
         const int64_t hidx = ha.index[h];
         const bool central = ha.central[h] == 1;
         double cur = ha.cur_r[h], r2max = 0.0;
-        int nloop = ha.nloop[h], nrows = 0, action = ACT_RETRY, n_rungs = 1;
+        // a list longer than the scratch provisioned for it (rounds are enqueued before their list sizes are known):
+        // the surplus moves on like halos that do not fit the tier
+        int nloop = ha.nloop[h], nrows = 0, action = it < slot_cap ? ACT_RETRY : ACT_OVERFLOW, n_rungs = 1;
         uint32_t n = 0, total = 0, n_gather = 0;
         double r2rung[4] = {-1.0, -1.0, -1.0, -1.0};  // squared radii of the gathered rungs, accepted rung first
         bool look1 = false;  // the look-ahead sphere did not fit: sweep the current rung alone
@@ -586,7 +588,7 @@ int launch_front(soap_chunk* c, const DevCfg& cfg, const HaloArrays& ha, const u
     if (grid > need) grid = need < 1 ? 1 : need;
     LAUNCH_N(h, CAP <= 256 ? "k_tier_front<256>" : "k_tier_front<1024>", kern, grid, 32 * NW, smem, stream, c->v, ha, cfg,
              list, n_list, overflow, n_overflow, queue_cursor, try_list, ctr, recs, pids, item_minr, item_minfof,
-             bank_stride, multi, (unsigned long long)n_upper * CAP);
+             bank_stride, multi, n_upper, (unsigned long long)n_upper * CAP);
     return 0;
 }
 
