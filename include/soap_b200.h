@@ -165,8 +165,9 @@ typedef struct {
      * computed from the particles already loaded without asking for a larger radius. */
     double ap_prev_radius[SOAP_MAX_APERTURES];
     double proj_prev_radius[SOAP_MAX_APERTURES];
-    /* cross-check switches, 0 in production: bit 0 = route every halo through the general
-     * (kernel-sequence) path instead of the small-halo tiers */
+    /* cross-check / measurement switches, 0 in production: bit 0 = route every halo through the general
+     * (kernel-sequence) path instead of the small-halo tiers; bit 1 = launch every kernel on the caller's
+     * stream, one after the other, instead of overlapping tiers, scan variants and the general path */
     uint32_t debug_flags;
 } soap_halo_config;
 

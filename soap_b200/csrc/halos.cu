@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(TB, 3) k_count(ChunkView v, HaloArrays ha, con
         double msum[NLOOK];
 #pragma unroll
         for (int k = 0; k < NLOOK; k++) { cnt[k] = 0; msum[k] = 0.0; }
-        sweep_item(v, S, cx, cy, cz, r, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS>(v, S, cx, cy, cz, r, im, [&](uint32_t t, bool ok) {
             if (ok) {
                 const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
                 if (r2 <= r2k[nr - 1]) {
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(TB) k_collect(ChunkView v, HaloArrays ha, DevC
         unsigned long long minr = ~0ull;
         int minfof = -1;
         const bool dmo = cfg.dmo != 0;
-        sweep_item(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_IDS | SW_TYPE>(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             bool in = false;
             Rec rec;
             uint32_t fb = 0;
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(TB) k_pj_bins(ChunkView v, HaloArrays ha, DevC
         uint32_t* fc = fine_cnt + pl.fine_off[h];
         const int64_t* fex = FILL ? fine_excl + pl.fine_off[h] : nullptr;
         const bool dmo = cfg.dmo != 0;
-        sweep_item(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_TYPE>(v, S, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             if (!ok || v.grnr[t] != hidx) return;
             const double r2 = periodic_r2(v.px[t], v.py[t], v.pz[t], cx, cy, cz, L, halfL);
             if (!(r2 <= r2max)) return;
@@ -1088,6 +1088,9 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     TierLims tl;
     // projected apertures and the general-path cross-check switch keep every halo out of the tiers
     const bool tiers_on = dc.n_pj == 0 && !(cfg->debug_flags & 1u);
+    // measurement switch: every kernel on the caller's stream, one after the other (per-kernel event times then
+    // measure work, not residency next to the kernels of other streams)
+    const bool serial = (cfg->debug_flags & 2u) != 0;
     for (int t = 0; t < 3; t++) tl.lim[t] = tiers_on ? tier_nexp[t < NTIER ? t : NTIER - 1] : -1;
     for (int t = 0; t < 3; t++)
         if (tl.lim[t] >= TIER_BUCKETS) SOAP_FAIL("soap_process_halos: tier limit above %d", TIER_BUCKETS - 1);
@@ -1146,7 +1149,7 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
         if (n_up[0] + n_up[1] > 0) {
             CUDA_TRY(cudaEventRecord(h->ev_tfork, stream));
             for (int t = 0; t < NTIER; t++) {
-                cudaStream_t ts = h->tstream[t];
+                cudaStream_t ts = serial ? stream : h->tstream[t];
                 CUDA_TRY(cudaStreamWaitEvent(ts, h->ev_tfork, 0));
                 if (n_up[t] == 0) continue;
                 const int rounds = TIER_ROUNDS + t;
@@ -1332,18 +1335,20 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                 // clusters of 8 and of 16 CTAs.  Forked onto side streams they overlap -- the giants' clusters keep a
                 // few SMs busy for milliseconds while the rest of the GPU does everything else.
                 if (h->side_init()) SOAP_FAIL("soap_process_halos: cannot create side streams");
+                cudaStream_t sd[3];
+                for (int i = 0; i < 3; i++) sd[i] = serial ? stream : h->side[i];
                 CUDA_TRY(cudaEventRecord(h->ev_fork, stream));
-                for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
+                for (int i = 0; i < 3; i++) CUDA_TRY(cudaStreamWaitEvent(sd[i], h->ev_fork, 0));
                 if (hc.n_huge > 0) {
                     // clusters of 16 CTAs (non-portable size): the largest halo is the critical path of this phase
                     unsigned int ncl = hc.n_huge < (unsigned)(sm / SCAN_CS_HUGE) ? hc.n_huge : (unsigned)(sm / SCAN_CS_HUGE);
                     if (cfg->dmo) {
                         CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<2, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                        LAUNCH(h, (k_scan_solve<2, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, h->side[0], ha, dc, huge_list,
+                        LAUNCH(h, (k_scan_solve<2, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, sd[0], ha, dc, huge_list,
                                &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
                     } else {
                         CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<8, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                        LAUNCH(h, (k_scan_solve<8, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, h->side[0], ha, dc, huge_list,
+                        LAUNCH(h, (k_scan_solve<8, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, sd[0], ha, dc, huge_list,
                                &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
                     }
                 }
@@ -1351,26 +1356,26 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                     // one cluster of SCAN_CS CTAs per large halo
                     unsigned int ncl = hc.n_big < (unsigned)(sm * 2 / SCAN_CS) ? hc.n_big : (unsigned)(sm * 2 / SCAN_CS);
                     if (cfg->dmo)
-                        LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, h->side[1], ha, dc, big_list,
+                        LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, sd[1], ha, dc, big_list,
                                &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
                     else
-                        LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, h->side[1], ha, dc, big_list,
+                        LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, sd[1], ha, dc, big_list,
                                &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
                 }
                 if (hc.n_try > 0) {
                     unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
                     if (cfg->dmo)
-                        LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, h->side[2], ha, dc, try_list, n_try_dev, recs, next,
+                        LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, sd[2], ha, dc, try_list, n_try_dev, recs, next,
                                ctr, item_minr, item_minfof);
                     else
-                        LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, h->side[2], ha, dc, try_list, n_try_dev, recs, next,
+                        LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, sd[2], ha, dc, try_list, n_try_dev, recs, next,
                                ctr, item_minr, item_minfof);
                 }
                 if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr,
                                           item_minfof, 0, stream))
                     return -1;
                 for (int i = 0; i < 3; i++) {
-                    CUDA_TRY(cudaEventRecord(h->ev_join[i], h->side[i]));
+                    CUDA_TRY(cudaEventRecord(h->ev_join[i], sd[i]));
                     CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i], 0));
                 }
             }

@@ -320,10 +320,18 @@ struct SweepShared {
     unsigned long long pos_next;
 };
 
+// Fields of the next chunk a sweep asks to have prefetched into L1 while it works on the current one
+// (positions always; the rest is what the kernel reads of the particles that pass the radius test).
+enum : unsigned { SW_MASS = 1u, SW_VEL = 2u, SW_IDS = 4u, SW_TYPE = 8u };
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Sweep the candidates of work item im with the whole CTA (SWEEP_NT threads).
 // f(t, ok) is called warp-synchronously: all 32 lanes of a warp call it
 // together, ok tells whether particle slot t is a real candidate of the lane.
-template <class F>
+// A warp's chunks ascend, so the row piece of a chunk is found by walking on
+// from the previous one; the chunk after the current one is located first and
+// its particle fields are prefetched, so that f's loads do not wait on HBM.
+template <unsigned PREF = 0u, class F>
 __device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx, double cy, double cz,
                                   double r, const Item& im, F f) {
     constexpr int NT = SWEEP_NT, NW = SWEEP_NT / 32;
@@ -370,14 +378,28 @@ __device__ inline void sweep_item(const ChunkView& v, SweepShared& S, double cx,
         if (threadIdx.x == 0) S.cpre[0] = 0;
         __syncthreads();
         const uint32_t total = S.cpre[NT];
-        for (uint32_t c = wid; c < total; c += NW) {
-            int jl = 0, jh = NT;  // largest jl with cpre[jl] <= c
-            while (jh - jl > 1) {
-                const int mid = (jl + jh) >> 1;
-                if (S.cpre[mid] <= c) jl = mid; else jh = mid;
-            }
+        int jl = 0;  // largest jl with cpre[jl] <= c; cpre[NT] = total > c ends the walk
+        auto locate = [&](uint32_t c, uint32_t& t, bool& ok) {
+            while (S.cpre[jl + 1] <= c) jl++;
             const uint32_t off = (c - S.cpre[jl]) * 32u + (uint32_t)lane;
-            f(S.s0[jl] + off, off < S.len[jl]);
+            t = S.s0[jl] + off;
+            ok = off < S.len[jl];
+            if (ok) {
+                prefetch_l1(v.px + t); prefetch_l1(v.py + t); prefetch_l1(v.pz + t);
+                if (PREF & SW_MASS) prefetch_l1(v.mass + t);
+                if (PREF & SW_VEL) { prefetch_l1(v.vx + t); prefetch_l1(v.vy + t); prefetch_l1(v.vz + t); }
+                if (PREF & SW_IDS) { prefetch_l1(v.grnr + t); prefetch_l1(v.fof + t); }
+                if (PREF & SW_TYPE) prefetch_l1(v.type + t);
+            }
+        };
+        uint32_t c = (uint32_t)wid, t_cur = 0, t_nxt = 0;
+        bool ok_cur = false, ok_nxt = false;
+        if (c < total) locate(c, t_cur, ok_cur);
+        while (c < total) {
+            const uint32_t cn = c + NW;
+            if (cn < total) locate(cn, t_nxt, ok_nxt);
+            f(t_cur, ok_cur);
+            c = cn; t_cur = t_nxt; ok_cur = ok_nxt;
         }
         pos_base = S.pos_next;
         row_base += NT;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TB, 3) k_it_accum(ChunkView v, HaloArrays ha, 
         const double R = ha.cur_r[h];
         const double halfL = 0.5 * v.L, L = v.L;
         const int64_t hidx = ha.index[h];
-        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_IDS | SW_TYPE>(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             double r2 = 0.0, x = 0.0, y = 0.0, z = 0.0, m = 0.0, nrm = 1.0;
             uint32_t tbit = 0;
             bool bound = false;

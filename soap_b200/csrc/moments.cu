@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(TB, (V <= 16 && NTY == 1) ? 3 : 1) k_moments(C
         const int32_t cen_fof = sr->cen_fof;
         BankAcc<V> ba;
         ba.init(gbank_stride);
-        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_VEL | SW_IDS | SW_TYPE>(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             bool in = false;
             int key = 0;
             double val[V];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(TB, 3) k_kappa(ChunkView v, HaloArrays ha, Dev
         __syncthreads();
         const int ns = nsel;
         if (ns == 0) continue;
-        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_VEL | SW_IDS | SW_TYPE>(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             if (!ok) return;
             const uint32_t tc = (uint32_t)v.type[t];
             if (tc != 0u && tc != 2u) return;  // gas and stars only

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TB) k_projected(ChunkView v, HaloArrays ha, De
         __syncthreads();
         BankAcc<PV> ba;
         ba.init();
-        sweep_item(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
+        sweep_item<SW_MASS | SW_VEL | SW_IDS | SW_TYPE>(v, SW, cx, cy, cz, R, im, [&](uint32_t t, bool ok) {
             bool in = false;
             double x = 0, y = 0, z = 0, m = 0, vx = 0, vy = 0, vz = 0;
             int tcode = 0;
