@@ -715,9 +715,10 @@ def main():
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")))
-        per_step = tr.get(args.workload, {}).get(dom)
-        if per_step is not None:  # the table holds the sum over one step's launches
-            traffic = round(per_step / max(modelled[dom]["launches_per_step"], 1.0))
+        captured = tr.get(args.workload, {}).get(dom)
+        n_cap = tr.get(args.workload + "_launches", {}).get(dom)
+        if captured is not None and n_cap:  # bytes per captured launch
+            traffic = round(captured / n_cap)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": modelled[dom]["achieved_gbs"], "peak": peak,

@@ -65,6 +65,7 @@ constexpr int SCAN_CS_HUGE = 16;
 // spheres of up to 256 / 1024 particles); larger ones take the general path
 constexpr long long SMALL_NEXP_0 = 150, SMALL_NEXP_1 = 500;
 constexpr int TIER_ROUNDS = 5;
+constexpr unsigned int SEQ_MIN_LIST = 2048;  // general path: shorter lists of small halos are scanned CTA-wise
 
 struct Bucket {
     unsigned long long start;
@@ -835,14 +836,14 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(SCAN_NT, NCH == 2 ?
                  const unsigned int* __restrict__ n_try, const Rec* __restrict__ recs,
                  uint32_t* __restrict__ next, Counters* ctr,
                  const unsigned long long* __restrict__ item_minr,
-                 const int32_t* __restrict__ item_minfof) {
+                 const int32_t* __restrict__ item_minfof, int cursor_slot) {
     __shared__ ScanShared<NCH, SCAN_NT> S;
     __shared__ unsigned int s_it;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int n_list = *n_try;
     // dynamic queue: the lists are roughly largest-first, and a cluster that drew a 5-million-record halo must not
     // also own every 37th of the rest
-    unsigned int* cursor = &ctr->scan_cursor[CS > 8 ? 2 : (CS > 1 ? 1 : 0)];
+    unsigned int* cursor = &ctr->scan_cursor[cursor_slot];
     while (true) {
         if (CS > 1) {
             if (cluster.block_rank() == 0 && threadIdx.x == 0) s_it = atomicAdd(cursor, 1u);
@@ -1345,11 +1346,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                     if (cfg->dmo) {
                         CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<2, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
                         LAUNCH(h, (k_scan_solve<2, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, sd[0], ha, dc, huge_list,
-                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
+                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof, 2);
                     } else {
                         CUDA_TRY(cudaFuncSetAttribute(k_scan_solve<8, SCAN_CS_HUGE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
                         LAUNCH(h, (k_scan_solve<8, SCAN_CS_HUGE>), ncl * SCAN_CS_HUGE, SCAN_NT, 0, sd[0], ha, dc, huge_list,
-                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof);
+                               &ctr->n_huge, recs, next, ctr, item_minr, item_minfof, 2);
                     }
                 }
                 if (hc.n_big > 0) {
@@ -1357,23 +1358,34 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
                     unsigned int ncl = hc.n_big < (unsigned)(sm * 2 / SCAN_CS) ? hc.n_big : (unsigned)(sm * 2 / SCAN_CS);
                     if (cfg->dmo)
                         LAUNCH(h, (k_scan_solve<2, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, sd[1], ha, dc, big_list,
-                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof, 1);
                     else
                         LAUNCH(h, (k_scan_solve<8, SCAN_CS>), ncl * SCAN_CS, SCAN_NT, 0, sd[1], ha, dc, big_list,
-                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof);
+                               &ctr->n_big, recs, next, ctr, item_minr, item_minfof, 1);
                 }
                 if (hc.n_try > 0) {
                     unsigned int g = hc.n_try < (unsigned)(sm * 8) ? hc.n_try : (unsigned)(sm * 8);
                     if (cfg->dmo)
                         LAUNCH(h, (k_scan_solve<2, 1>), g, SCAN_NT, 0, sd[2], ha, dc, try_list, n_try_dev, recs, next,
-                               ctr, item_minr, item_minfof);
+                               ctr, item_minr, item_minfof, 0);
                     else
                         LAUNCH(h, (k_scan_solve<8, 1>), g, SCAN_NT, 0, sd[2], ha, dc, try_list, n_try_dev, recs, next,
-                               ctr, item_minr, item_minfof);
+                               ctr, item_minr, item_minfof, 0);
                 }
-                if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr, item_minr,
-                                          item_minfof, 0, stream))
-                    return -1;
+                // the smallest halos: a thread each when there are thousands of them (tiers off, projected apertures);
+                // a few dozen stragglers would be one long sequential tail on an idle GPU: a CTA each instead
+                if (hc.n_seq >= SEQ_MIN_LIST) {
+                    if (soap_launch_solve_seq(c, dc, ha, seq_list, &ctr->n_seq, hc.n_seq, recs, next, &ctr->n_next, ctr,
+                                              item_minr, item_minfof, 0, stream))
+                        return -1;
+                } else if (hc.n_seq > 0) {
+                    if (cfg->dmo)
+                        LAUNCH(h, (k_scan_solve<2, 1>), hc.n_seq, SCAN_NT, 0, stream, ha, dc, seq_list, &ctr->n_seq, recs, next,
+                               ctr, item_minr, item_minfof, 3);
+                    else
+                        LAUNCH(h, (k_scan_solve<8, 1>), hc.n_seq, SCAN_NT, 0, stream, ha, dc, seq_list, &ctr->n_seq, recs, next,
+                               ctr, item_minr, item_minfof, 3);
+                }
                 for (int i = 0; i < 3; i++) {
                     CUDA_TRY(cudaEventRecord(h->ev_join[i], sd[i]));
                     CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_join[i], 0));

@@ -184,7 +184,8 @@ struct Counters {
     unsigned long long rec_single, rec_total;
     unsigned int n_bkt_small, n_bkt_big, n_bkt_huge, n_items;
     unsigned int n_mslot, items_overflow, n_bslot, n_seq;
-    unsigned int scan_cursor[3], n_huge;  // dynamic queues of k_scan_solve (CTA / cluster of 8 / cluster of 16 lists)
+    unsigned int scan_cursor[4], n_huge;  // dynamic queues of k_scan_solve (CTA / cluster of 8 / cluster of 16 lists,
+                                          // [3]: a short list of small halos scanned CTA-wise)
     unsigned long long pairs, candidates, count_pairs, mom_pairs;
     unsigned long long rec_class[4];  // records of the halos scanned by: thread, CTA, cluster of 8, cluster of 16
 };

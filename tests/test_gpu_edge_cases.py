@@ -45,6 +45,23 @@ def test_missing_particle_types_and_int64_ids():
     _run(data, H, cp, SO4[:2], aps, flags=1 | 2 | 4 | 8, dmo=False)
 
 
+def test_int64_ids_outside_int32_are_an_error():
+    """membership is an integer-exact contract (halo_tasks.py:121-123): a 64-bit group id that does not fit the
+    int32 the device keeps must be refused, not wrapped onto another halo's id"""
+    from soap_b200 import _lib
+    from soap_b200.halo_tasks import DeviceChunk
+
+    L = 20.0
+    data, H = synth.dummy_chunk(912, 5, boxsize=L, n_background=2000, npart_choices=(10, 100))
+    data = {t: d for t, d in data.items() if t in (0, 1)}
+    for d in data.values():
+        d["GroupNr_bound"] = d["GroupNr_bound"].astype(np.int64)
+        d["FOFGroupIDs"] = d["FOFGroupIDs"].astype(np.int64)
+    data[1]["GroupNr_bound"][3] = (1 << 32) + 7  # would alias halo 7 after narrowing
+    with pytest.raises(_lib.SoapError, match="32 bits"):
+        DeviceChunk(data, L)
+
+
 def _handmade_chunk(L):
     """A few dark matter halos built by hand in an otherwise thin uniform background."""
     rng = np.random.default_rng(42)
