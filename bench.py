@@ -56,7 +56,7 @@ M_PART = {"config4": 0.0843 * (25.0 / 284.4) ** 3 * 512**3 / (2 * 376**3)}
 HYDRO_TYPES = {0: 0.45, 1: 0.50, 4: 0.049, 5: 0.001}
 SEED = 20261018
 SO_LIST = None  # filled in main (needs synth)
-VOLUME_SLABS = 256  # slabs per dimension of the ghost-shell cover of the one-volume runs (N > 1)
+VOLUME_SLABS = 256  # cells per dimension of the ghost-shell cover (chunk_tasks.cell_cover) of the one-volume runs (N > 1)
 CPU_SAMPLE_FRACTION = 0.05  # volume fraction of the fixed central sub-cube the CPU arm processes
 
 # Algorithmic bytes per unit of every kernel.  unit = which counter the kernel's work is
@@ -446,7 +446,7 @@ def main():
         data, halos = synth.volume_chunk(cat, mine["index"], device=gen_dev, cells_per_dim=VOLUME_SLABS)
         n_own = int(sum(len(d["Masses"]) for d in data.values()))
         wl_name = (f"{args.workload} x {world}: ONE synthetic DMO volume, L={Lv:.1f} Mpc, {n_part * world} particles, "
-                   f"{n_halos_total} halos, cut into {world} Peano-Hilbert chunks with ghost shells (slab cover of the read "
+                   f"{n_halos_total} halos, cut into {world} Peano-Hilbert chunks with ghost shells (cell cover of the read "
                    f"spheres), one per GPU, particles generated per chunk on the device; SO 200_crit/200_mean/500_crit/BN98 "
                    f"+ BoundSubhalo")
         L = Lv

@@ -112,71 +112,65 @@ def chunk_halos(halo, chunk_size, c):
     return {k: v[off[c] : off[c + 1]] for k, v in halo.items()}
 
 
+def cell_cover(cofp, read_radius, boxsize, cells_per_dim=64):
+    """Which cells of a ``cells_per_dim``^3 grid of the box are touched by some halo's cube
+    [c - r, c + r]^3 (periodic): bool [n, n, n].  This is the reference's read mask (mask_cells.py:6-38 marks,
+    per halo, the SWIFT cells that overlap its read region), rasterised for all halos at once with a 3-D
+    difference array."""
+    cofp = np.asarray(cofp, dtype=np.float64).reshape(-1, 3)
+    rr = np.asarray(read_radius, dtype=np.float64).reshape(-1, 1)
+    n = int(cells_per_dim)
+    cs = boxsize / n
+    if len(cofp) == 0:
+        return np.zeros((n, n, n), dtype=bool)
+    lo = np.floor((cofp - rr) / cs).astype(np.int64)
+    ext = np.floor((cofp + rr) / cs).astype(np.int64) - lo + 1
+    full = ext >= n  # the cube spans the whole axis
+    lo = np.where(full, 0, lo % n)  # in [0, n)
+    hi1 = lo + np.where(full, n, ext)  # exclusive end, <= 2n: the wrapped part lies in the second period
+    diff = np.zeros((2 * n + 1,) * 3, dtype=np.int32)
+    for sx in (0, 1):
+        for sy in (0, 1):
+            for sz in (0, 1):
+                ix = hi1[:, 0] if sx else lo[:, 0]
+                iy = hi1[:, 1] if sy else lo[:, 1]
+                iz = hi1[:, 2] if sz else lo[:, 2]
+                np.add.at(diff, (ix, iy, iz), -1 if (sx + sy + sz) & 1 else 1)
+    cov = diff.cumsum(axis=0).cumsum(axis=1).cumsum(axis=2)[: 2 * n, : 2 * n, : 2 * n] > 0
+    del diff
+    cov = cov[:n] | cov[n:]
+    cov = cov[:, :n] | cov[:, n:]
+    return np.ascontiguousarray(cov[:, :, :n] | cov[:, :, n:])
+
+
+def _cells_of(pos, boxsize, n, xp):
+    cs = boxsize / n
+    if xp is np:
+        return np.clip(np.floor((pos % boxsize) / cs).astype(np.int64), 0, n - 1)
+    import torch
+
+    return torch.clamp(torch.floor(torch.remainder(pos, boxsize) / cs).to(torch.int64), 0, n - 1)
+
+
 def ghost_mask(pos, cofp, read_radius, boxsize, cells_per_dim=64):
-    """Particles that must travel with a chunk.  Like the reference, which reads
-    whole SWIFT cells overlapping a halo's read sphere (mask_cells.py:6-38), the
-    box is cut into cells and a particle is kept if its cell lies, in every
-    dimension, in a slab touched by some halo's [c - r, c + r] (periodic): a
-    superset of the cells the reference would read."""
+    """Particles that must travel with a chunk: like the reference, which reads the SWIFT cells overlapping
+    a halo's read region (mask_cells.py:6-38), the box is cut into cells and a particle is kept if its cell is
+    touched by some halo's cube [c - r, c + r]^3 (``cell_cover``)."""
     pos = np.asarray(pos, dtype=np.float64)
-    cofp = np.asarray(cofp, dtype=np.float64)
-    rr = np.asarray(read_radius, dtype=np.float64)
-    n = int(cells_per_dim)
-    cs = boxsize / n
-    keep = np.ones(pos.shape[0], dtype=bool)
-    for d in range(3):
-        lo = np.floor((cofp[:, d] - rr) / cs).astype(np.int64)
-        hi = np.floor((cofp[:, d] + rr) / cs).astype(np.int64)
-        if np.any(hi - lo + 1 >= n):
-            continue  # some halo touches every slab of this axis
-        shift = (-lo.min() // n + 1) * n  # make indices non-negative without changing them mod n
-        lo, hi = lo + shift, hi + shift
-        diff = np.zeros(int(hi.max()) + 2, dtype=np.int64)
-        np.add.at(diff, lo, 1)
-        np.add.at(diff, hi + 1, -1)
-        covered = np.cumsum(diff)[:-1] > 0
-        slab = np.zeros(n, dtype=bool)
-        idx = np.nonzero(covered)[0] % n
-        slab[idx] = True
-        cell = np.clip(np.floor((pos[:, d] % boxsize) / cs).astype(np.int64), 0, n - 1)
-        keep &= slab[cell]
-    return keep
-
-
-def slab_cover(cofp, read_radius, boxsize, cells_per_dim=64):
-    """Per dimension, which of the ``cells_per_dim`` slabs of the box are touched by some halo's
-    [c - r, c + r] (periodic): bool [3, cells_per_dim]."""
-    cofp = np.asarray(cofp, dtype=np.float64)
-    rr = np.asarray(read_radius, dtype=np.float64)
-    n = int(cells_per_dim)
-    cs = boxsize / n
-    out = np.ones((3, n), dtype=bool)
-    for d in range(3):
-        lo = np.floor((cofp[:, d] - rr) / cs).astype(np.int64)
-        hi = np.floor((cofp[:, d] + rr) / cs).astype(np.int64)
-        if np.any(hi - lo + 1 >= n):
-            continue
-        shift = (-lo.min() // n + 1) * n
-        lo, hi = lo + shift, hi + shift
-        diff = np.zeros(int(hi.max()) + 2, dtype=np.int64)
-        np.add.at(diff, lo, 1)
-        np.add.at(diff, hi + 1, -1)
-        slab = np.zeros(n, dtype=bool)
-        slab[np.nonzero(np.cumsum(diff)[:-1] > 0)[0] % n] = True
-        out[d] = slab
-    return out
+    cover = cell_cover(cofp, read_radius, boxsize, cells_per_dim)
+    cell = _cells_of(pos, boxsize, int(cells_per_dim), np)
+    return cover[cell[:, 0], cell[:, 1], cell[:, 2]]
 
 
 def ghost_mask_device(pos, cofp, read_radius, boxsize, cells_per_dim=64):
-    """``ghost_mask`` for positions that are already on the device (torch [N,3]): the slab cover is a few
-    hundred bytes computed on the host from the chunk's halos, the per-particle test runs where the
-    particles are.  Returns a bool tensor on pos.device."""
+    """``ghost_mask`` for positions that are already on the device (torch [N,3]): the cell cover is computed on the
+    host from the chunk's halos (a few MB), the per-particle test runs where the particles are.  Returns a bool
+    tensor on pos.device."""
     import torch
 
-    cover = torch.as_tensor(slab_cover(cofp, read_radius, boxsize, cells_per_dim), device=pos.device)
-    cs = boxsize / cells_per_dim
-    cell = torch.clamp(torch.floor(torch.remainder(pos, boxsize) / cs).to(torch.int64), 0, cells_per_dim - 1)
-    return cover[0][cell[:, 0]] & cover[1][cell[:, 1]] & cover[2][cell[:, 2]]
+    cover = torch.as_tensor(cell_cover(cofp, read_radius, boxsize, cells_per_dim), device=pos.device)
+    cell = _cells_of(pos, boxsize, int(cells_per_dim), torch)
+    return cover[cell[:, 0], cell[:, 1], cell[:, 2]]
 
 
 def gather_tables(table, index, dst=0, group=None):

@@ -441,19 +441,23 @@ def volume_catalogue(n_part, n_halos, boxsize, seed=20261018, m_part=0.0843, min
                 search_radius=np.maximum(1.01 * r200, 1.0e-3), read_radius=np.maximum(1.01 * r200, 5.0))
 
 
-def volume_chunk(cat, halo_sel, device="cpu", cells_per_dim=64, sort_cells=32):
+def volume_chunk(cat, halo_sel, device="cpu", cells_per_dim=64, sort_cells=32, full_cover=False):
     """Particles and halo arrays of one chunk of the volume: ``halo_sel`` = catalogue rows of the chunk's halos.
     Returns (data, halos) like nfw_chunk (torch tensors on ``device``), the particles being every particle of the
-    volume that lies in the chunk's slab cover (chunk_tasks.slab_cover of the chunk's read spheres)."""
+    volume that lies in the chunk's cell cover (chunk_tasks.cell_cover of the chunk's read regions)."""
     import torch
 
-    from .chunk_tasks import slab_cover
+    from .chunk_tasks import cell_cover
 
     L, seed = cat["boxsize"], cat["seed"]
     halo_sel = np.asarray(halo_sel)
-    cover = slab_cover(cat["cofp"][halo_sel], cat["read_radius"][halo_sel], L, cells_per_dim)
+    cover3 = cell_cover(cat["cofp"][halo_sel], cat["read_radius"][halo_sel], L, cells_per_dim)
+    if full_cover:  # every particle of the volume, also those no halo of the selection can reach
+        cover3[:] = True
+    cover = [cover3.any(axis=(1, 2)), cover3.any(axis=(0, 2)), cover3.any(axis=(0, 1))]  # per-axis projections
     cs = L / cells_per_dim
-    # halos that reach into the covered region: some covered slab within [c - R, c + R] in every dimension
+    # halos that may reach into the covered region: some covered slab within [c - R, c + R] in every dimension
+    # (a superset; the per-particle cut below is exact)
     R = cat["outer_factor"] * cat["r200"]
     touch = np.ones(len(R), dtype=bool)
     for d in range(3):
@@ -496,15 +500,15 @@ def volume_chunk(cat, halo_sel, device="cpu", cells_per_dim=64, sort_cells=32):
     rb = torch.zeros(len(hs), dtype=torch.float64, device=device)
     rb.scatter_reduce_(0, hid[bound], r[bound], reduce="amax", include_self=True)
     # keep what lies in the region
-    cov = torch.as_tensor(cover, device=device)
+    cov = torch.as_tensor(cover3, device=device)
     cell = torch.clamp(torch.floor(pos / cs).to(torch.int64), 0, cells_per_dim - 1)
-    keep = cov[0][cell[:, 0]] & cov[1][cell[:, 1]] & cov[2][cell[:, 2]]
+    keep = cov[cell[:, 0], cell[:, 1], cell[:, 2]]
     pos, gid_k = pos[keep], gid[keep]
     grnr = torch.where(bound, ghid, torch.full_like(ghid, -1))[keep].to(torch.int32)
     fof = ghid[keep].to(torch.int32)
     del cell, keep, hid, local, bound, r, ghid, gid
     # background of the covered cells
-    idx = np.flatnonzero((cover[0][:, None, None] & cover[1][None, :, None] & cover[2][None, None, :]).ravel())
+    idx = np.flatnonzero(cover3.ravel())
     assert cat["bg_cells"] == cells_per_dim
     cnt = t(cat["bg_count"][idx], torch.int64)
     nb = int(cnt.sum().item())

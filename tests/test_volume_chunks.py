@@ -16,7 +16,7 @@ def _rows(pos):
 def test_chunks_hold_the_volumes_particles_of_their_region():
     L = 60.0
     cat = synth.volume_catalogue(300000, 600, L, seed=5, max_np=20000)
-    whole, Hw = synth.volume_chunk(cat, cat["index"])
+    whole, Hw = synth.volume_chunk(cat, cat["index"], full_cover=True)
     pw = whole[1]["Coordinates"].numpy()
     assert len(pw) == 300000 and len(_rows(pw)) == 300000
     H = {k: cat[k] for k in ("cofp", "index", "search_radius", "read_radius", "nr_bound_part", "is_central")}
@@ -29,7 +29,7 @@ def test_chunks_hold_the_volumes_particles_of_their_region():
         pc = data[1]["Coordinates"].numpy()
         total += len(pc)
         assert _rows(pc) <= all_rows  # every particle of the chunk is a particle of the volume, bit for bit
-        # the chunk is exactly the volume cut by its slab cover
+        # the chunk is exactly the volume cut by its cell cover
         keep = ct.ghost_mask(pw, halos["cofp"].numpy(), halos["read_radius"].numpy(), L)
         assert len(pc) == int(keep.sum())
         g = data[1]["GroupNr_bound"].numpy()
