@@ -256,7 +256,7 @@ def make_sample(data_np, H_np, L, frac=CPU_SAMPLE_FRACTION, margin=6.0):
     Hs = {k: v[hsel] for k, v in H_np.items()}
     ds = {}
     for t, d in data_np.items():
-        p = d["Coordinates"]
+        p = np.mod(d["Coordinates"], L)  # chunks of a decomposed volume are box-wrapped around their reference position
         psel = np.all((p >= lo - margin) & (p < hi + margin), axis=1)
         ds[t] = {k: np.ascontiguousarray(v[psel]) for k, v in d.items()}
     return ds, Hs, side, margin, np.flatnonzero(hsel), int(in_cube.sum() - hsel.sum())
@@ -445,6 +445,16 @@ def main():
         mine = ct.chunk_halos(hs, csz, ct.assign_chunks(len(csz), world)[rank][0])
         data, halos = synth.volume_chunk(cat, mine["index"], device=gen_dev, cells_per_dim=VOLUME_SLABS)
         n_own = int(sum(len(d["Masses"]) for d in data.values()))
+        if have_cuda:
+            # stage A1 of the path, as ChunkTask does after reading a chunk (chunk_tasks.py:210-215,284-288): particles
+            # are wrapped to the periodic copies nearest the chunk's reference position, so that the ghost shell that
+            # reaches across the box edge does not stretch the mesh over the whole box
+            from soap_b200.shared_mesh import box_wrap
+
+            c_np = mine["cofp"]
+            ref_pos = 0.5 * (c_np.min(axis=0) + c_np.max(axis=0))
+            for d in data.values():
+                box_wrap(d["Coordinates"], ref_pos, Lv)
         wl_name = (f"{args.workload} x {world}: ONE synthetic DMO volume, L={Lv:.1f} Mpc, {n_part * world} particles, "
                    f"{n_halos_total} halos, cut into {world} Peano-Hilbert chunks with ghost shells (cell cover of the read "
                    f"spheres), one per GPU, particles generated per chunk on the device; SO 200_crit/200_mean/500_crit/BN98 "

@@ -151,6 +151,9 @@ int soap_chunk_create(soap_handle* h, const soap_ptype_arrays* types, int n_type
     int res = (int)cbrt((double)n / (double)fine_ppc);
     if (res < 1) res = 1;
     if (res > 512) res = 512;
+    // 256^3 blocked cell ids fit 24 bits = three 8-bit radix passes; a slightly finer mesh would pay a fourth pass over
+    // every (key, index) pair for less than twice the particles per cell
+    if (res > 256 && res <= 320) res = 256;
     ChunkView& v = c->v;
     v.n = n;
     v.L = boxsize;
