@@ -1101,6 +1101,11 @@ int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_hal
     unsigned long long total_pairs = 0, total_cand = 0, total_count_pairs = 0, total_try_pairs = 0, total_mom_pairs = 0;
     for (int t = 0; t < 3; t++) c->last_tier_pairs[t] = 0;
     bool tiers_running = false;
+    // a failed call must not leave tier kernels in flight on their own streams (they use the handle's workspace)
+    struct TierGuard {
+        const bool& running;
+        ~TierGuard() { if (running) cudaDeviceSynchronize(); }
+    } tier_guard{tiers_running};
     unsigned int n_pend_first = 0;
     if (tiers_on) {
         LAUNCH(h, k_tier_scan, 1, TIER_BUCKETS, 0, stream, size_hist, tier_n, tl);
