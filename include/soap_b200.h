@@ -184,7 +184,12 @@ int64_t soap_result_layout(const soap_halo_config* cfg, char* buf, int64_t bufle
  * [n_halo,3]).  out_dev is float64 [n_halo, ncol] row-major (ncol from
  * soap_result_layout), status_dev int32 [n_halo].  For halos that end with
  * SOAP_HALO_RADIUS_TOO_SMALL the updated search/read radii
- * (halo_tasks.py:166-181,390-402) are in the InputHalos columns.  Syncs. */
+ * (halo_tasks.py:166-181,390-402) are in the InputHalos columns.  Syncs:
+ * the work is ordered after what is queued on `stream` and complete when the
+ * call returns; internally the small-halo tiers and the scan variants run on
+ * streams of the handle next to the general path on `stream` (events order
+ * them; debug_flags bit 1 puts everything on `stream`).  One call at a time
+ * per handle. */
 int soap_process_halos(soap_chunk* c, const soap_halo_config* cfg, int64_t n_halo,
                        const double* cofp_dev, const double* search_radius_dev,
                        const double* read_radius_dev, const int64_t* index_dev,
