@@ -291,6 +291,55 @@ class ChunkFeed:
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(self.device)
 
+    @staticmethod
+    def _host_buffers(arrays):
+        out = []
+        for v in arrays.values() if isinstance(arrays, dict) else arrays:
+            if isinstance(v, dict):
+                out += ChunkFeed._host_buffers(v)
+            elif hasattr(v, "full"):  # SharedArray
+                out.append(v.full)
+            else:
+                out.append(v)
+        return out
+
+    def register(self, arrays):
+        """Page-lock host buffers in place (cudaHostRegister) so that ``upload`` runs at the PCIe rate.  SOAP's
+        particle arrays live in MPI shared windows (SOAP/core/shared_array.py:33), i.e. pageable memory that
+        ``tensor.pin_memory()`` would have to copy; registration pins the window itself, once per buffer.
+        ``arrays``: (nested) dict or list of numpy arrays / CPU tensors / SharedArrays.  Returns a token for
+        ``unregister``."""
+        import numpy as np
+        import torch
+
+        rt = torch.cuda.cudart()
+        token = []
+        for a in self._host_buffers(arrays):
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda or a.is_pinned() or a.numel() == 0:
+                    continue
+                ptr, nbytes = a.data_ptr(), a.numel() * a.element_size()
+            else:
+                a = np.asarray(a)
+                if a.size == 0 or not a.flags["C_CONTIGUOUS"]:
+                    continue
+                ptr, nbytes = a.ctypes.data, a.nbytes
+            err = rt.cudaHostRegister(ptr, nbytes, 0)
+            if int(err) != 0:
+                for p in token:
+                    rt.cudaHostUnregister(p)
+                raise _lib.SoapError(f"cudaHostRegister of {nbytes} bytes failed with error {int(err)}")
+            token.append(ptr)
+        return token
+
+    def unregister(self, token):
+        import torch
+
+        rt = torch.cuda.cudart()
+        for p in token:
+            rt.cudaHostUnregister(p)
+        token.clear()
+
     def upload(self, data_host, halos_host):
         """Start the upload; returns a ticket for ``wait``."""
         import torch
