@@ -64,7 +64,10 @@ def make_chunk(seed, n_halos, n_background):
     return data, H
 
 
-def build_reference(filters_cfg, so_list, ap_list, proj_list, subhalo_props, so_props, ap_props, proj_props):
+def build_reference(filters_cfg, so_list, ap_list, proj_list, subhalo_props, so_props, ap_props, proj_props, cosmo=None):
+    """cosmo: optional overrides of the module's unit system {BOX, CRIT, OMEGA_M, SOFT, H_INT}"""
+    c_ = dict(BOX=BOX, CRIT=CRIT, OMEGA_M=OMEGA_M, SOFT=SOFT, H_INT=H_INT)
+    c_.update(cosmo or {})
     rs.install()
     import SOAP.core.shared_array as sa
 
@@ -90,11 +93,12 @@ def build_reference(filters_cfg, so_list, ap_list, proj_list, subhalo_props, so_
             raise KeyError(name)
 
     cellgrid = types.SimpleNamespace(
-        snap_unit_registry=None, critical_density=ua(CRIT), mean_density=ua(CRIT * OMEGA_M), a=1.0,
-        a_unit=rs._Units(), z=0.0, boxsize=ua(BOX), baryon_softening=ua(SOFT), dark_matter_softening=ua(SOFT),
-        nu_softening=ua(SOFT), observer_position=ua([0.5 * BOX] * 3), snapshot_datasets=Datasets(),
-        cosmology={"Omega_nu_0": 0.0, "H0 [internal units]": H_INT, "H [internal units]": H_INT, "Omega_g": 0.0,
-                   "Omega_m": OMEGA_M}, virBN98=177.65, get_unit=lambda name: rs._Units(),
+        snap_unit_registry=None, critical_density=ua(c_["CRIT"]), mean_density=ua(c_["CRIT"] * c_["OMEGA_M"]), a=1.0,
+        a_unit=rs._Units(), z=0.0, boxsize=ua(c_["BOX"]), baryon_softening=ua(c_["SOFT"]),
+        dark_matter_softening=ua(c_["SOFT"]), nu_softening=ua(c_["SOFT"]), observer_position=ua([0.5 * c_["BOX"]] * 3),
+        snapshot_datasets=Datasets(),
+        cosmology={"Omega_nu_0": 0.0, "H0 [internal units]": c_["H_INT"], "H [internal units]": c_["H_INT"], "Omega_g": 0.0,
+                   "Omega_m": c_["OMEGA_M"]}, virBN98=177.65, get_unit=lambda name: rs._Units(),
     )
 
     def enabled(cls, wanted):

@@ -138,6 +138,8 @@ def unyt_quantity(value=0.0, units=None, dtype=None, registry=None, **kw):
 
 
 class UnitRegistry:
+    lut = {}
+
     def __init__(self, *a, **k):
         pass
 
@@ -215,7 +217,13 @@ def install():
         return _Units()
 
     u.__getattr__ = _unit_attr
-    _module("unyt.dimensions").__getattr__ = lambda name: 1
+    dims = _module("unyt.dimensions")
+    dims.__getattr__ = lambda name: 1
+    u.dimensions = dims
+    # what SOAP/core/swift_units.py (unit_registry_from_snapshot) touches: registries and unit definitions are no-ops
+    u.unit_registry = types.SimpleNamespace(UnitRegistry=UnitRegistry)
+    u.define_unit = lambda *a, **k: None
+    u.UnitSystem = lambda *a, **k: None
     _module("unyt.array", unyt_array=unyt_array, unyt_quantity=unyt_quantity)
     _module("unyt.physical_constants").__getattr__ = lambda name: unyt_array(1.0)
     mpi = types.SimpleNamespace(MIN="min", MAX="max", SUM="sum", COMM_WORLD=_Comm(), COMM_TYPE_SHARED=0,

@@ -3,6 +3,7 @@ were produced by executing the reference's own function bodies
 (tests/golden/make_golden.py, run in the build container).  CPU only."""
 
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -140,23 +141,8 @@ def _class_fixture():
     return gen, g, data, H
 
 
-def test_oracle_reproduces_reference_classes():
-    from tests import _compare as cmp
-
-    gen, g, data, H = _class_fixture()
-    cp = gen.cosmology_params()
-    so_cfg = [s.split(":") for s in g["config/so"]]
-    ap_cfg = [s.split(":") for s in g["config/ap"]]
-    pj_cfg = [s.split(":") for s in g["config/proj"]]
-    so = [(t, 177.65 if t == "BN98" else float(v)) for t, v, _ in so_cfg]
-    aps = [(float(k), float(k) * 1e-3, int(i)) for k, i, _ in ap_cfg]
-    proj = [(float(k), float(k) * 1e-3) for k, _ in pj_cfg]
-    filters = {"general": (int(g["config/filter_general_limit"]), (0, 1, 4, 5))}
-    out, props = cmp.run_oracle(data, H, cp, so, aps, faithful=True, projected=proj, filters=filters,
-                                so_filters=[f for _, _, f in so_cfg], ap_filters=[f for _, _, f in ap_cfg],
-                                proj_filters=[f for _, f in pj_cfg], mesh_resolution=8,
-                                skip_gt=("exclusive", "inclusive", "projected"))
-    # reference group name of each oracle prop
+def _reference_group_names(props, so_cfg, ap_cfg, pj_cfg, aps):
+    """reference group name(s) of each oracle property object"""
     names = {}
     k = a = j = 0
     for p in props:
@@ -176,38 +162,105 @@ def test_oracle_reproduces_reference_classes():
             kpc = sorted(float(x[0]) for x in pj_cfg)[j]
             names[p.group_name] = [f"ProjectedAperture/{kpc:.0f}kpc/proj{ax}" for ax in "xyz"]
             j += 1
+    return names
+
+
+def _check_halo(g, i, res, info, ih, err, props, names, worst):
+    """oracle result of fixture halo i against what the reference returned; returns (values checked, zero groups)"""
     done = g["done"]
+    n_checked = n_zero_groups = 0
+    if done[i] == -1:
+        return 0, 0  # the reference itself aborts on this halo (SO_properties.py:457, see make_golden_classes.py)
+    assert (res is not None) == bool(done[i]), (i, err)
+    # the radius the halo asks for next time (halo_tasks.py:166-181)
+    assert float(ih["search_radius"]) == float(g["search_radius_out"][i]), i
+    if res is None:
+        return 0, 0
+    assert info["n_loop"] == int(g["n_loop"][i]), (i, info["n_loop"], int(g["n_loop"][i]))
+    for p in props:
+        for ref_group, ogroup in zip(names[p.group_name], [p.group_name] if len(names[p.group_name]) == 1 else
+                                     [f"{p.group_name}/proj{ax}" for ax in "xyz"]):
+            blk = res.get(ogroup, {})
+            keys = [key[len("val/" + ref_group) + 1:] for key in g.files if key.startswith("val/" + ref_group + "/")]
+            assert keys, ref_group
+            if not blk:
+                n_zero_groups += 1
+            for name in keys:
+                ref = np.asarray(g[f"val/{ref_group}/{name}"][i], dtype=np.float64)
+                got = np.zeros_like(ref) if name not in blk or blk[name] is None else \
+                    np.asarray(blk[name], dtype=np.float64).reshape(ref.shape)
+                n_checked += 1
+                if ref.dtype.kind in "iu" or name.startswith("N"):
+                    assert np.array_equal(got, ref), (i, ref_group, name, got, ref)
+                    continue
+                # reference outputs are float32 (CentreOfMass float64): a few float32 ulps of the column scale
+                sc = max(float(np.max(np.abs(ref))), 1e-30)
+                e = float(np.max(np.abs(got - ref))) / sc
+                worst[name] = max(worst.get(name, 0.0), e)
+                assert e <= 2e-6, (i, ref_group, name, got, ref, e)
+    return n_checked, n_zero_groups
+
+
+def _fixture_config(g):
+    so_cfg = [s.split(":") for s in g["config/so"]]
+    ap_cfg = [s.split(":") for s in g["config/ap"]]
+    pj_cfg = [s.split(":") for s in g["config/proj"]]
+    so = [(t, 177.65 if t == "BN98" else float(v)) for t, v, _ in so_cfg]
+    aps = [(float(k), float(k) * 1e-3, int(i)) for k, i, _ in ap_cfg]
+    proj = [(float(k), float(k) * 1e-3) for k, _ in pj_cfg]
+    filters = {"general": (int(g["config/filter_general_limit"]), (0, 1, 4, 5))}
+    return so_cfg, ap_cfg, pj_cfg, so, aps, proj, filters
+
+
+def test_oracle_reproduces_reference_classes():
+    from tests import _compare as cmp
+
+    gen, g, data, H = _class_fixture()
+    cp = gen.cosmology_params()
+    so_cfg, ap_cfg, pj_cfg, so, aps, proj, filters = _fixture_config(g)
+    out, props = cmp.run_oracle(data, H, cp, so, aps, faithful=True, projected=proj, filters=filters,
+                                so_filters=[f for _, _, f in so_cfg], ap_filters=[f for _, _, f in ap_cfg],
+                                proj_filters=[f for _, f in pj_cfg], mesh_resolution=8,
+                                skip_gt=("exclusive", "inclusive", "projected"))
+    names = _reference_group_names(props, so_cfg, ap_cfg, pj_cfg, aps)
     n_checked = n_zero_groups = 0
     worst = {}
     for i, (res, info, ih, err) in enumerate(out):
-        if done[i] == -1:
-            continue  # the reference itself aborts on this halo (SO_properties.py:457, see make_golden_classes.py)
-        assert (res is not None) == bool(done[i]), (i, err)
-        # the radius the halo asks for next time (halo_tasks.py:166-181)
-        assert float(ih["search_radius"]) == float(g["search_radius_out"][i]), i
-        if res is None:
-            continue
-        assert info["n_loop"] == int(g["n_loop"][i]), (i, info["n_loop"], int(g["n_loop"][i]))
-        for p in props:
-            for ref_group, ogroup in zip(names[p.group_name], [p.group_name] if len(names[p.group_name]) == 1 else
-                                         [f"{p.group_name}/proj{ax}" for ax in "xyz"]):
-                blk = res.get(ogroup, {})
-                keys = [key[len("val/" + ref_group) + 1:] for key in g.files if key.startswith("val/" + ref_group + "/")]
-                assert keys, ref_group
-                if not blk:
-                    n_zero_groups += 1
-                for name in keys:
-                    ref = np.asarray(g[f"val/{ref_group}/{name}"][i], dtype=np.float64)
-                    got = np.zeros_like(ref) if name not in blk or blk[name] is None else \
-                        np.asarray(blk[name], dtype=np.float64).reshape(ref.shape)
-                    n_checked += 1
-                    if ref.dtype.kind in "iu" or name.startswith("N"):
-                        assert np.array_equal(got, ref), (i, ref_group, name, got, ref)
-                        continue
-                    # reference outputs are float32 (CentreOfMass float64): a few float32 ulps of the column scale
-                    sc = max(float(np.max(np.abs(ref))), 1e-30)
-                    e = float(np.max(np.abs(got - ref))) / sc
-                    worst[name] = max(worst.get(name, 0.0), e)
-                    assert e <= 2e-6, (i, ref_group, name, got, ref, e)
+        a, b = _check_halo(g, i, res, info, ih, err, props, names, worst)
+        n_checked += a
+        n_zero_groups += b
     assert n_checked > 3000 and n_zero_groups > 0  # filtered / satellite groups are exact zeros in both
     print("class-level parity: values", n_checked, "worst", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+
+
+# tests/golden/halo_refgen.npz: the same pinning on the reference's OWN test halos (BASELINE config 1), drawn by
+# its unmodified tests/dummy_halo_generator.py (DummyHaloGenerator(4251), lengths x 40 to one unit system) and
+# processed one halo per chunk by the reference's process_single_halo (tests/golden/make_golden_refgen.py).
+def test_oracle_reproduces_reference_on_its_own_fixture_halos():
+    import importlib.util
+
+    from tests import _compare as cmp
+
+    spec = importlib.util.spec_from_file_location("make_golden_refgen", os.path.join(GOLD, "make_golden_refgen.py"))
+    gen = importlib.util.module_from_spec(spec)
+    sys.path.insert(0, GOLD)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(GOLD, "halo_refgen.npz"))
+    cp = gen.cosmology_params(g)
+    so_cfg, ap_cfg, pj_cfg, so, aps, proj, filters = _fixture_config(g)
+    n_checked = n_zero_groups = n_done = 0
+    worst = {}
+    for i in range(len(g["done"])):
+        data, H = gen.fixture_halo(g, i)
+        out, props = cmp.run_oracle(data, H, cp, so, aps, faithful=True, projected=proj, filters=filters,
+                                    so_filters=[f for _, _, f in so_cfg], ap_filters=[f for _, _, f in ap_cfg],
+                                    proj_filters=[f for _, f in pj_cfg], mesh_resolution=4,
+                                    skip_gt=("exclusive", "inclusive", "projected"))
+        names = _reference_group_names(props, so_cfg, ap_cfg, pj_cfg, aps)
+        res, info, ih, err = out[0]
+        a, b = _check_halo(g, i, res, info, ih, err, props, names, worst)
+        n_checked += a
+        n_zero_groups += b
+        n_done += int(g["done"][i] == 1)
+    assert n_done >= 10 and n_checked > 1500
+    print("reference fixture halos: done", n_done, "values", n_checked, "worst", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
