@@ -30,8 +30,9 @@ import make_golden_classes as mgc  # noqa: E402
 import ref_standin as rs  # noqa: E402
 
 LSCALE = 40.0
-N_HALOS = 20
-NPART = [1, 10, 100, 1000]
+N_HALOS = 22
+NPART = [1, 10, 100, 1000, 10000]  # tests/test_SO_properties.py draws from the same list
+MAX_BIG = 2  # halos of 10 000 particles kept (450 KB of input each); further ones are drawn and skipped
 SO_LIST = [(20000.0, "crit", "basic"), (50000.0, "crit", "basic"), (50000.0, "mean", "general")]
 AP_LIST = [(1.0, False, "basic"), (1.0, True, "basic"), (3.0, False, "general"), (3.0, True, "basic")]
 PROJ_LIST = [(1.0, "basic"), (3.0, "basic")]
@@ -73,6 +74,7 @@ def main():
     out = {f"cosmo/{k}": v for k, v in cosmo.items()}
     cp = cosmology_params({k: np.asarray(v) for k, v in out.items()})
     halos = []
+    n_big = 0
     while len(halos) < N_HALOS:
         ih, data, rmax, Mtot, Npart, pn = gen.get_random_halo(NPART)
         d = {}
@@ -87,6 +89,10 @@ def main():
                         FOFGroupIDs=np.asarray(data[pt]["FOFGroupIDs"], dtype=np.int32).copy())
         if not d:
             continue
+        if sum(len(x["Masses"]) for x in d.values()) > 5000:
+            if n_big >= MAX_BIG:
+                continue
+            n_big += 1
         idx = int(ih["index"])
         nb = sum(int((x["GroupNr_bound"] == idx).sum()) for x in d.values())
         r = float(rmax) * LSCALE
