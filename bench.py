@@ -79,9 +79,9 @@ KERNEL_MODEL = {
     "k_fine_hist_halo": (24, "rec"),
     "k_collect": (49, "rec"),              # 33 in, 16 record out
     "k_sort_bins": (32, "rec"),            # 16 in, 16 out
-    "k_scan_solve<1>": (16, "rec_cta"),        # CTA per halo; <8> / <16>: clusters of 8 / 16 CTAs per halo (the three run
-    "k_scan_solve<8>": (16, "rec_c8"),        # concurrently on side streams, each on its own size class of halos: their
-    "k_scan_solve<16>": (16, "rec_c16"),       # times overlap and are not additive)
+    "k_scan_solve<1>": (16, "rec_cta"),        # CTA per halo; <8> / <16>: clusters of 8 / 16 CTAs per halo, each on its own
+    "k_scan_solve<8>": (16, "rec_c8"),        # size class of halos (concurrent on side streams in the timed region, one after
+    "k_scan_solve<16>": (16, "rec_c16"),       # the other in the instrumented pass the table is taken from)
     "k_moments": (48, "mom"),              # position 24, mass 4, velocity 12, grnr 4, fof 4
     "k_projected": (48, "mom"),
     "k_kappa": (48, "mom"),
