@@ -10,17 +10,20 @@ A *step* is one pass of the hot path over one chunk: cell-list build + reorder
 scans / moment reductions (stage B+C) for every halo of the chunk.  Workload at
 N=1 is BASELINE.json configs[1]: synthetic DMO chunk, 512^3 particles,
 2e5 halos, L=284.4, SO {200_crit, 200_mean, 500_crit, BN98} + BoundSubhalo
-(SURVEY.md 8(d).2).  For N>1 every rank gets its own chunk of that recipe
-(seed + rank): chunks are independent units; the only
-collective is the gather of the per-halo result tables to rank 0 (weak scaling).
+(SURVEY.md 8(d).2).  For N>1 the ranks share ONE periodic volume of N times that recipe:
+a global halo catalogue, Peano-Hilbert chunks with ghost shells (one per rank), particles
+generated per chunk on the device and box-wrapped around the chunk's reference position
+(BASELINE config 5's shape).  No data-path collective; a float32 copy of
+the per-rank result tables is gathered to rank 0 asynchronously (weak scaling).
 
 `value`   halos/s with the chunk's raw arrays already resident in HBM.
 `e2e`     the same metric through the host-buffer API: pinned host arrays ->
           H2D -> kernels -> D2H of the result table, all inside the timed region.
-`roofline` for the kernel phase with the largest share of the step, from CUDA
-          events recorded by the library on the launching stream.
-`cpu_baseline` the numpy oracle port of the reference path on the host cores,
-          on a bounded sub-chunk of the same workload.
+`roofline` / `kernels`  per kernel, from an instrumented pass after the timed region:
+          CUDA events around every launch with every kernel on one stream
+          (soap_halo_config.debug_flags bit 1); `roofline` is the kernel with the most time.
+`cpu_baseline` the numpy oracle port of the reference path on the host cores, on a fixed
+          sub-cube of the same chunk; `parity` compares the GPU table of the timed step with it.
 """
 
 import argparse
